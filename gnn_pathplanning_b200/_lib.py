@@ -1,0 +1,142 @@
+"""ctypes binding of libgnnpp_b200.so (C ABI in include/gnnpp_b200.h) + in-tree build.
+
+There is NO CPU fallback: if the shared library is missing, cannot be loaded, or a
+call fails, a RuntimeError (or AssertionError for shape errors, matching the
+reference's `assert`s) is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libgnnpp_b200.so")
+SOURCES = ("graph_filter.cu", "planner.cu")
+HEADERS = ("common.cuh",)
+INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200.h")
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+GPP_OK = 0
+GPP_ERR_INVALID = -1
+GPP_ERR_UNSUPPORTED = -2
+FEATURE_MAJOR = 0   # [B, G, N]  (reference API layout)
+NODE_MAJOR = 1      # [B, N, G]
+
+# every symbol include/gnnpp_b200.h declares
+EXPORTED = (
+    "gpp_last_error", "gpp_abi_version", "gpp_device_info",
+    "gpp_graph_filter_workspace_bytes", "gpp_graph_filter_forward",
+    "gpp_graph_filter_backward_workspace_bytes", "gpp_graph_filter_backward",
+    "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
+    "gpp_planner_forward", "gpp_planner_forward_host",
+    "gpp_launch_count", "gpp_reset_launch_count",
+)
+
+
+class PlannerWeights(C.Structure):
+    _fields_ = [
+        ("conv_w", C.c_void_p * 5), ("conv_b", C.c_void_p * 5),
+        ("bn_w", C.c_void_p * 5), ("bn_b", C.c_void_p * 5),
+        ("bn_mean", C.c_void_p * 5), ("bn_var", C.c_void_p * 5),
+        ("compress_w", C.c_void_p), ("compress_b", C.c_void_p),
+        ("gf_w", C.c_void_p), ("gf_b", C.c_void_p),
+        ("action_w", C.c_void_p), ("action_b", C.c_void_p),
+    ]
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC_DIR, s) for s in SOURCES + HEADERS] + [INCLUDE]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles the CUDA sources for sm_100a into the in-tree shared library."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Returns the loaded library; raises RuntimeError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "gnn_pathplanning_b200: %s is missing -- build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                "There is no CPU fallback for this package." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+        lib.gpp_last_error.restype = C.c_char_p
+        lib.gpp_last_error.argtypes = []
+        lib.gpp_abi_version.restype = i
+        lib.gpp_device_info.argtypes = [C.POINTER(i)] * 3
+        lib.gpp_graph_filter_workspace_bytes.restype = sz
+        lib.gpp_graph_filter_workspace_bytes.argtypes = [i, i, i]
+        lib.gpp_graph_filter_forward.restype = i
+        lib.gpp_graph_filter_forward.argtypes = [vp, vp, i, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp]
+        lib.gpp_graph_filter_backward_workspace_bytes.restype = sz
+        lib.gpp_graph_filter_backward_workspace_bytes.argtypes = [i, i, i, i, i]
+        lib.gpp_graph_filter_backward.restype = i
+        lib.gpp_graph_filter_backward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp,
+                                                  i, i, i, i, i, i, i, i, vp, vp]
+        lib.gpp_planner_create.restype = i
+        lib.gpp_planner_create.argtypes = [C.POINTER(vp), i]
+        lib.gpp_planner_destroy.restype = None
+        lib.gpp_planner_destroy.argtypes = [vp]
+        lib.gpp_planner_set_weights.restype = i
+        lib.gpp_planner_set_weights.argtypes = [vp, C.POINTER(PlannerWeights), i, vp]
+        lib.gpp_planner_forward.restype = i
+        lib.gpp_planner_forward.argtypes = [vp, vp, vp, i, vp, vp, i, i, vp]
+        lib.gpp_planner_forward_host.restype = i
+        lib.gpp_planner_forward_host.argtypes = [vp, vp, vp, i, vp, i, i]
+        lib.gpp_launch_count.restype = C.c_ulonglong
+        lib.gpp_launch_count.argtypes = []
+        lib.gpp_reset_launch_count.restype = None
+        lib.gpp_reset_launch_count.argtypes = []
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc == GPP_OK:
+        return
+    msg = load().gpp_last_error().decode("utf-8", "replace")
+    if rc == GPP_ERR_INVALID:
+        raise AssertionError("libgnnpp_b200: " + msg)
+    if rc == GPP_ERR_UNSUPPORTED:
+        raise NotImplementedError("libgnnpp_b200: " + msg)
+    raise RuntimeError("libgnnpp_b200 (status %d): %s" % (rc, msg))
+
+
+def launch_count() -> int:
+    return int(load().gpp_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().gpp_reset_launch_count()

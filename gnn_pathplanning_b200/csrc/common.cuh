@@ -1,0 +1,90 @@
+// Shared helpers for libgnnpp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/gnnpp_b200.h"
+
+namespace gpp {
+
+// ---- error plumbing -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local unsigned long long g_launches;
+
+#define GPP_CUDA_OK(expr)                                                                  \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::gpp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                             __FILE__, __LINE__);                                          \
+            return GPP_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+#define GPP_REQUIRE(cond, code, ...)                                                       \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            ::gpp::set_error(__VA_ARGS__);                                                 \
+            return code;                                                                   \
+        }                                                                                  \
+    } while (0)
+
+#define GPP_LAUNCH_CHECK()                                                                 \
+    do {                                                                                   \
+        ::gpp::g_launches++;                                                               \
+        GPP_CUDA_OK(cudaGetLastError());                                                   \
+    } while (0)
+
+int sm_count();
+
+// ---- device-side PTX helpers (Blackwell: mbarrier + 1-D bulk async copy = UBLKCP) -----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// generic-proxy writes/reads of smem must be ordered before async-proxy (bulk copy) writes
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+__device__ __forceinline__ float4 ld_smem4(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+
+}  // namespace gpp

@@ -1,0 +1,242 @@
+"""Drop-in `DecentralPlannerNet` backed by libgnnpp_b200.so.
+
+Same module surface as /root/reference/graphs/models/decentralplanner.py:13-318:
+`DecentralPlannerNet(config)` reading config.num_agents / config.nGraphFilterTaps,
+identical submodule names (`ConvLayers`, `compressMLP`, `GFL`, `actionsMLP`) and hence
+identical `state_dict` keys/shapes and initial values under the same torch seed,
+`addGSO(S)` with S [B,N,N], `forward(x)` with x [B,N,3,11,11] returning the reference's
+Python list of N tensors [B,5].
+
+Execution:
+  * eval mode under torch.no_grad()  -> gpp_planner_forward: two kernels (agent-tiled
+    CNN+compress feature extractor; fused graph filter + ReLU + action MLP), logits
+    written agent-major so the returned list is N views of one buffer.
+  * otherwise (training / autograd)   -> agents batched into one [B*N,...] pass per layer
+    with the reference's PER-AGENT BatchNorm statistics and sequential running-stat
+    updates reproduced exactly, and the fused graph-filter kernels (forward + backward)
+    through torch.autograd.
+CUDA only: the module raises if asked to run on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as Fn
+
+from . import _lib
+from .graphml import GraphFilterBatch, graph_filter, NODE_MAJOR, _require_cuda
+
+_CONV_CH = [3, 32, 32, 64, 64, 128]
+_CONV_IDX = (0, 4, 7, 11, 14)
+
+
+def weights_init(m):
+    """Same rule as /root/reference/graphs/weights_initializer.py:11-23 (matched on the
+    class name): Conv* / Linear -> xavier-normal weight (Linear bias 0); BatchNorm* ->
+    weight N(1, 0.02), bias 0."""
+    name = m.__class__.__name__
+    if 'Conv' in name:
+        nn.init.xavier_normal_(m.weight)
+    elif 'BatchNorm' in name:
+        m.weight.data.normal_(1.0, 0.02)
+        m.bias.data.fill_(0.0)
+    elif 'Linear' in name:
+        nn.init.xavier_normal_(m.weight)
+        m.bias.data.fill_(0.0)
+
+
+class _NativePlanner:
+    """Owns one gpp_planner handle (per device) and keeps its weight arena in sync."""
+
+    def __init__(self, K: int):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.gpp_planner_create(C.byref(h), K))
+        self.handle = h
+        self.key = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.gpp_planner_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class DecentralPlannerNet(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.S = None
+        self.numAgents = self.config.num_agents
+        K = self.config.nGraphFilterTaps
+
+        layers = []
+        for l in range(5):
+            layers.append(nn.Conv2d(_CONV_CH[l], _CONV_CH[l + 1], kernel_size=3, stride=1, padding=1, bias=True))
+            layers.append(nn.BatchNorm2d(_CONV_CH[l + 1]))
+            layers.append(nn.ReLU(inplace=True))
+            if l % 2 == 0:
+                layers.append(nn.MaxPool2d(kernel_size=2))
+        self.ConvLayers = nn.Sequential(*layers)
+        self.compressMLP = nn.Sequential(nn.Linear(128, 128, bias=True), nn.ReLU(inplace=True))
+        self.numFeatures2Share = 128
+
+        self.L = 1
+        self.F = [128, 128]
+        self.K = [K]
+        self.E = 1
+        self.bias = True
+        self.GFL = nn.Sequential(GraphFilterBatch(128, 128, K, self.E, self.bias), nn.ReLU(inplace=True))
+        self.actionsMLP = nn.Sequential(nn.Linear(128, 5, bias=True))
+        self.apply(weights_init)
+        self._native = {}
+
+    def __getstate__(self):
+        # native handles are per-process device resources: never pickled / deep-copied
+        d = self.__dict__.copy()
+        d["_native"] = {}
+        return d
+
+    # ------------------------------------------------------------------ API
+    def addGSO(self, S):
+        assert len(S.shape) == 3
+        self.S = S.unsqueeze(1)
+
+    def forward(self, inputTensor) -> List[torch.Tensor]:
+        _require_cuda(inputTensor, "inputTensor")
+        assert inputTensor.dim() == 5 and tuple(inputTensor.shape[2:]) == (3, 11, 11)
+        assert self.S is not None, "addGSO(S) must be called before forward"
+        B, N = inputTensor.shape[0], inputTensor.shape[1]
+        assert self.S.shape[0] == B and self.S.shape[2] == N and self.S.shape[3] == N
+        S = self.S
+        if not S.is_cuda:
+            S = S.to(inputTensor.device)
+        self.GFL[0].addGSO(S)
+        if not self.training and not torch.is_grad_enabled():
+            logits = self._forward_fused(inputTensor, S)           # [N,B,5]
+        else:
+            logits = self._forward_autograd(inputTensor, S)        # [N,B,5]
+        return list(logits.unbind(0))
+
+    # ------------------------------------------------------- fused inference
+    def _weights_key(self):
+        ts = [p for p in self.parameters()] + [b for b in self.buffers()]
+        return tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _native_for(self, device) -> _NativePlanner:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        nat = self._native.get(idx)
+        if nat is None:
+            with torch.cuda.device(idx):
+                nat = _NativePlanner(self.K[0])
+            self._native[idx] = nat
+        key = self._weights_key()
+        if nat.key != key:
+            w = _lib.PlannerWeights()
+            for l, ci in enumerate(_CONV_IDX):
+                conv, bn = self.ConvLayers[ci], self.ConvLayers[ci + 1]
+                w.conv_w[l] = conv.weight.data_ptr()
+                w.conv_b[l] = conv.bias.data_ptr()
+                w.bn_w[l] = bn.weight.data_ptr()
+                w.bn_b[l] = bn.bias.data_ptr()
+                w.bn_mean[l] = bn.running_mean.data_ptr()
+                w.bn_var[l] = bn.running_var.data_ptr()
+            lin, gf, act = self.compressMLP[0], self.GFL[0], self.actionsMLP[0]
+            w.compress_w, w.compress_b = lin.weight.data_ptr(), lin.bias.data_ptr()
+            w.gf_w, w.gf_b = gf.weight.data_ptr(), gf.bias.data_ptr()
+            w.action_w, w.action_b = act.weight.data_ptr(), act.bias.data_ptr()
+            for t in list(self.parameters()) + list(self.buffers()):
+                if t.is_floating_point():
+                    _require_cuda(t, "model parameter")
+                    assert t.is_contiguous() and t.dtype == torch.float32
+            _lib.check(nat.lib.gpp_planner_set_weights(
+                nat.handle, C.byref(w), 1, torch.cuda.current_stream().cuda_stream))
+            nat.key = key
+        return nat
+
+    def _forward_fused(self, x, S):
+        B, N = x.shape[0], x.shape[1]
+        nat = self._native_for(x.device)
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        S3 = S[:, 0]
+        if S3.dtype not in (torch.float32, torch.float64):
+            S3 = S3.float()
+        S3 = S3.contiguous()
+        logits = torch.empty(N, B, 5, device=x.device, dtype=torch.float32)
+        _lib.check(nat.lib.gpp_planner_forward(
+            nat.handle, x.data_ptr(), S3.data_ptr(), int(S3.dtype == torch.float64),
+            logits.data_ptr(), None, B, N, torch.cuda.current_stream().cuda_stream))
+        return logits
+
+    def infer_host(self, x_host: torch.Tensor, S_host: torch.Tensor, out_host: torch.Tensor = None,
+                   device=None) -> torch.Tensor:
+        """Rollout-step entry point on HOST tensors (pinned for full copy speed): H2D of
+        x [B,N,3,11,11] f32 and S [B,N,N] f32/f64, the fused forward, D2H of the logits,
+        all inside gpp_planner_forward_host.  Returns `out_host` [N,B,5] f32."""
+        assert not self.training, "infer_host is the eval-mode rollout path"
+        assert not x_host.is_cuda and not S_host.is_cuda
+        assert x_host.dtype == torch.float32 and x_host.is_contiguous() and S_host.is_contiguous()
+        assert S_host.dim() == 3
+        B, N = x_host.shape[0], x_host.shape[1]
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        nat = self._native_for(dev)
+        torch.cuda.current_stream(dev).synchronize()      # weight re-layout (if any) is done
+        if out_host is None:
+            out_host = torch.empty(N, B, 5, dtype=torch.float32).pin_memory()
+        assert S_host.dtype in (torch.float32, torch.float64)
+        with torch.cuda.device(dev):
+            _lib.check(nat.lib.gpp_planner_forward_host(
+                nat.handle, x_host.data_ptr(), S_host.data_ptr(), int(S_host.dtype == torch.float64),
+                out_host.data_ptr(), B, N))
+        return out_host
+
+    # ------------------------------------------------ autograd (training) path
+    def _bn_per_agent(self, h, bn, N):
+        """BatchNorm2d with the reference's per-agent semantics: the reference calls
+        ConvLayers once per agent (decentralplanner.py:284-286), so in train mode the batch
+        statistics are over (B,H,W) of ONE agent's slice and the running statistics are
+        updated N times per forward, in agent order.  h: [B*N, C, H, W] (b-major)."""
+        BN_, Cc, H, W = h.shape
+        B = BN_ // N
+        if not bn.training:
+            return Fn.batch_norm(h, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+        hv = h.view(B, N * Cc, H, W)
+        out = Fn.batch_norm(hv, None, None, bn.weight.repeat(N), bn.bias.repeat(N), True, 0.0, bn.eps)
+        if bn.track_running_stats:
+            with torch.no_grad():
+                cnt = B * H * W
+                var, mean = torch.var_mean(h.detach().view(B, N, Cc, H * W), dim=(0, 3), unbiased=False)
+                var_unb = var * (cnt / max(cnt - 1, 1))
+                m = bn.momentum
+                # running <- (1-m) running + m stat_i, applied for i = 0..N-1 in order
+                wts = m * (1.0 - m) ** torch.arange(N - 1, -1, -1, device=h.device, dtype=torch.float32)
+                decay = (1.0 - m) ** N
+                bn.running_mean.mul_(decay).add_((wts[:, None] * mean).sum(0))
+                bn.running_var.mul_(decay).add_((wts[:, None] * var_unb).sum(0))
+                bn.num_batches_tracked += N
+        return out.view(BN_, Cc, H, W)
+
+    def _forward_autograd(self, x, S):
+        B, N = x.shape[0], x.shape[1]
+        h = x.reshape(B * N, 3, 11, 11).float()
+        for l, ci in enumerate(_CONV_IDX):
+            conv, bn = self.ConvLayers[ci], self.ConvLayers[ci + 1]
+            h = Fn.conv2d(h, conv.weight, conv.bias, stride=1, padding=1)
+            h = Fn.relu(self._bn_per_agent(h, bn, N))
+            if l % 2 == 0:
+                h = Fn.max_pool2d(h, 2)
+        lin = self.compressMLP[0]
+        feat = Fn.relu(Fn.linear(h.reshape(B * N, 128), lin.weight, lin.bias)).view(B, N, 128)
+        gf = self.GFL[0]
+        shared = graph_filter(feat, S, gf.weight, gf.bias, fuse_relu=True,
+                              x_layout=NODE_MAJOR, y_layout=NODE_MAJOR)        # [B,N,128]
+        act = self.actionsMLP[0]
+        logits = Fn.linear(shared, act.weight, act.bias)                       # [B,N,5]
+        return logits.permute(1, 0, 2)

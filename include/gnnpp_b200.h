@@ -1,0 +1,155 @@
+/*
+ * gnnpp_b200.h -- C ABI of libgnnpp_b200.so: the B200 (sm_100a) implementation of the
+ * DecentralPlannerNet forward path of proroklab/gnn_pathplanning.
+ *
+ * The reference has no FFI of its own: its boundary for this path is the PyTorch
+ * nn.Module API.  This header is the C-level boundary a
+ * reference maintainer binds to (ctypes stub in INTEGRATION.md); every entry point
+ * names the reference code it replaces.  Plain pointers and sizes only -- no torch
+ * types.  All functions return 0 on success, a negative gpp_status otherwise;
+ * gpp_last_error() returns a thread-local human-readable message.
+ *
+ * Conventions
+ *   B batch (episodes), N agents (graph nodes), G input / F output features,
+ *   K filter taps, E = 1 edge feature (the only value the reference path constructs,
+ *   graphs/models/decentralplanner.py:209).
+ *   `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   "dev" pointers are device memory, "host" pointers are host memory (pinned for
+ *   full copy speed); neither is retained after the call returns unless stated.
+ */
+#ifndef GNNPP_B200_H
+#define GNNPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gpp_status {
+    GPP_OK = 0,
+    GPP_ERR_INVALID = -1,     /* bad argument / shape (the reference raises AssertionError) */
+    GPP_ERR_UNSUPPORTED = -2, /* valid in the reference but outside this library's envelope */
+    GPP_ERR_CUDA = -3,        /* CUDA runtime error (message has the cudaError string) */
+    GPP_ERR_NODEVICE = -4     /* no sm_100 device visible */
+} gpp_status;
+
+/* Tensor layouts of the node-signal tensors x / y. */
+typedef enum gpp_layout {
+    GPP_FEATURE_MAJOR = 0, /* [B, G, N]: the reference API layout (graphML.py:2298-2306) */
+    GPP_NODE_MAJOR = 1     /* [B, N, G]: the native layout between the fused stages */
+} gpp_layout;
+
+const char* gpp_last_error(void);
+int gpp_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+int gpp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------
+ * Graph filter  (replaces BatchLSIGF, utils/graphUtils/graphML.py:2273-2367, as called
+ * by GraphFilterBatch.forward :2458-2477)
+ *
+ *   z_0 = x ; z_k = z_{k-1} . S_b  (right multiplication, :2350)
+ *   y[b,f,n] = sum_{k,g} w[f,0,k,g] z_k[b,g,n] + bias[f]          (:2361-2366)
+ *
+ *   x      dev f32, layout x_layout, B*G*N
+ *   S      dev [B,N,N], f32 or (s_is_f64 != 0) f64 -- cast to f32 per element exactly as
+ *          `S.float()` does at :2350
+ *   w      dev f32 [F,1,K,G]  (the module's `weight`, untouched layout)
+ *   bias   dev f32 [F] or NULL
+ *   y      dev f32, layout y_layout, B*F*N
+ *   fuse_relu  apply max(.,0) in the epilogue (the nn.ReLU that follows the filter in
+ *          DecentralPlannerNet.GFL, decentralplanner.py:221)
+ *   workspace  dev scratch of gpp_graph_filter_workspace_bytes() bytes (holds the
+ *          k-major transposed taps); may be NULL only if that size is 0
+ * ---------------------------------------------------------------------------------- */
+size_t gpp_graph_filter_workspace_bytes(int G, int F, int K);
+
+int gpp_graph_filter_forward(const float* x, const void* S, int s_is_f64,
+                             const float* w, const float* bias, float* y,
+                             int B, int N, int G, int F, int K,
+                             int x_layout, int y_layout, int fuse_relu,
+                             void* workspace, void* stream);
+
+/* Backward of the same filter (replaces autograd through graphML.py:2342-2366).
+ *   dy   dev f32 [B,F,N]/[B,N,F] (y_layout) upstream gradient
+ *   y    dev f32, the forward OUTPUT (needed only when fuse_relu, for the mask), else NULL
+ *   dx   dev f32 out, x_layout         (NULL to skip)
+ *   dw   dev f32 out [F,1,K,G]         (NULL to skip; overwritten, not accumulated)
+ *   dbias dev f32 out [F]              (NULL to skip; overwritten)
+ *   workspace: gpp_graph_filter_backward_workspace_bytes() bytes of dev scratch.
+ * S receives no gradient (the reference's GSO never requires grad). */
+size_t gpp_graph_filter_backward_workspace_bytes(int B, int N, int G, int F, int K);
+
+int gpp_graph_filter_backward(const float* dy, const float* y, const float* x,
+                              const void* S, int s_is_f64, const float* w,
+                              float* dx, float* dw, float* dbias,
+                              int B, int N, int G, int F, int K,
+                              int x_layout, int y_layout, int fuse_relu,
+                              void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Whole-planner inference  (replaces DecentralPlannerNet.addGSO + forward in eval mode,
+ * graphs/models/decentralplanner.py:266-318: per-agent CNN + compress MLP -> K-tap graph
+ * filter + ReLU -> per-agent action MLP)
+ * ---------------------------------------------------------------------------------- */
+typedef struct gpp_planner gpp_planner;
+
+/* All pointers use the reference's state_dict shapes:
+ *   conv_w[l]  [C_{l+1}, C_l, 3, 3]   conv_b[l] [C_{l+1}]     C = 3,32,32,64,64,128
+ *   bn_w/bn_b/bn_mean/bn_var[l] [C_{l+1}]   (eval-mode BatchNorm2d, eps 1e-5)
+ *   compress_w [128,128] compress_b [128]; gf_w [128,1,K,128] gf_b [128] (from [128,1]);
+ *   action_w [5,128] action_b [5] */
+typedef struct gpp_planner_weights {
+    const float* conv_w[5];
+    const float* conv_b[5];
+    const float* bn_w[5];
+    const float* bn_b[5];
+    const float* bn_mean[5];
+    const float* bn_var[5];
+    const float* compress_w;
+    const float* compress_b;
+    const float* gf_w;
+    const float* gf_b;
+    const float* action_w;
+    const float* action_b;
+} gpp_planner_weights;
+
+/* K = number of graph-filter taps (config.nGraphFilterTaps, decentralplanner.py:131). */
+int gpp_planner_create(gpp_planner** out, int K);
+void gpp_planner_destroy(gpp_planner* p);
+
+/* Copies/re-lays-out the parameters into the planner's private device arena
+ * (k-major conv/linear weights, BatchNorm folded to per-channel scale/shift).
+ * `on_device` != 0: the pointers are device pointers, work is enqueued on `stream`;
+ * == 0: host pointers (synchronous). Call again whenever the parameters change. */
+int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights* w, int on_device,
+                            void* stream);
+
+/* Device-resident forward.
+ *   x       dev f32 [B,N,3,11,11]
+ *   S       dev [B,N,N] f32 / f64 (s_is_f64)
+ *   logits  dev f32 out [N,B,5]  -- agent-major, so that the reference's Python list of N
+ *           tensors [B,5] (decentralplanner.py:303-318) is N contiguous views
+ *   features_out  optional dev f32 [B,N,128] node-major CNN+compress features (may be NULL)
+ */
+int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_f64,
+                        float* logits, float* features_out, int B, int N, void* stream);
+
+/* Host-buffer forward: H2D copies of x and S, the forward, and the D2H copy of the logits
+ * all run on the planner's own stream; returns after the logits are in `logits_host`.
+ * This is the call a rollout loop makes once per step (agents/decentralplannerlocal.py
+ * :563-580 does the same with .to(device) + model(...)). */
+int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,
+                             int s_is_f64, float* logits_host, int B, int N);
+
+/* Number of kernels of this library launched by the calling thread's planner calls since
+ * the last reset (bench.py's gpu_launches claim is read from here, not guessed). */
+unsigned long long gpp_launch_count(void);
+void gpp_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNPP_B200_H */

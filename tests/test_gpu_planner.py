@@ -1,0 +1,124 @@
+"""GPU parity of the whole DecentralPlannerNet path against the reference-generated golden
+vectors and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+class Cfg:
+    def __init__(self, n, k):
+        self.num_agents, self.nGraphFilterTaps, self.device = n, k, torch.device("cuda")
+
+
+def _sd(g):
+    return {k[3:]: torch.from_numpy(np.ascontiguousarray(g[k])) for k in g.files if k.startswith("sd_")}
+
+
+def _model(sd, N, K):
+    import gnn_pathplanning_b200 as gp
+    m = gp.DecentralPlannerNet(Cfg(N, K))
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("f", ["planner_K3.npz", "planner_K2.npz"])
+def test_golden_eval(golden, f):
+    g = golden(f)
+    N, K, B = int(g["N"]), int(g["K"]), int(g["B"])
+    m = _model(_sd(g), N, K).eval()
+    x = torch.from_numpy(g["x"].astype(np.float32)).cuda()
+    S = torch.from_numpy(g["S"]).cuda()                 # f64 for K2 (rollout), f32 for K3
+    m.addGSO(S)
+    with torch.no_grad():
+        out = m(x)
+    assert isinstance(out, list) and len(out) == N and tuple(out[0].shape) == (B, 5)
+    got = torch.stack(out).cpu().numpy()
+    assert rel_err(got, g["eval_logits"]) <= TOL
+    assert np.array_equal(got.argmax(-1), g["eval_logits"].argmax(-1))
+    # host-buffer entry point (H2D + forward + D2H inside the C ABI call)
+    out_h = m.infer_host(torch.from_numpy(g["x"].astype(np.float32)).pin_memory(),
+                         torch.from_numpy(g["S"]).pin_memory())
+    assert rel_err(out_h.numpy(), g["eval_logits"]) <= TOL
+
+
+@pytest.mark.parametrize("f", ["planner_K3.npz", "planner_K2.npz"])
+def test_golden_train_step(golden, f):
+    from oracle import planner_oracle as po
+    g = golden(f)
+    N, K = int(g["N"]), int(g["K"])
+    m = _model(_sd(g), N, K).train()
+    x = torch.from_numpy(g["x"].astype(np.float32)).cuda()
+    S = torch.from_numpy(g["S"]).float().cuda()
+    m.addGSO(S)
+    out = m(x)
+    loss = po.planner_loss(out, torch.from_numpy(g["target"].astype(np.int64)).cuda())
+    loss.backward()
+    assert rel_err(torch.stack(out).detach().cpu().numpy(), g["train_logits"]) <= TOL
+    assert abs(loss.item() - float(g["train_loss"])) <= 1e-5 * max(1.0, abs(float(g["train_loss"])))
+    for n_, p in m.named_parameters():
+        # conv biases feed straight into a train-mode BatchNorm: their true gradient is 0 and
+        # both sides hold rounding noise there, so they are compared on an absolute scale
+        ref = g["grad_" + n_]
+        if n_.startswith("ConvLayers") and n_.endswith("bias") and int(n_.split(".")[1]) in (0, 4, 7, 11, 14):
+            assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-5
+        else:
+            assert rel_err(p.grad.cpu().numpy(), ref) <= 5e-5, n_
+    sd_after = m.state_dict()
+    for k in g.files:
+        if k.startswith("bn_after_"):
+            assert rel_err(sd_after[k[9:]].double().cpu().numpy(), g[k]) <= TOL, k
+
+
+@pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (20, 3, 24, 28), (40, 3, 16, 50), (1, 2, 5, 8),
+                                         (64, 3, 3, 50), (10, 1, 9, 20), (3, 3, 301, 12)])
+def test_eval_vs_oracle(N, K, B, map_w):
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    sd = po.init_state_dict(K, seed=N * 7 + K)
+    po.randomize_bn_stats(sd, seed=B)
+    m = _model(sd, N, K).eval()
+    x, S = synthetic.make_batch(B, N, map_w, seed=B + N)
+    xt, St = torch.from_numpy(x), torch.from_numpy(S)
+    with torch.no_grad():
+        ref = torch.stack(po.planner_forward(sd, St, xt)).numpy()
+        m.addGSO(St.cuda())
+        got = torch.stack(m(xt.cuda())).cpu().numpy()
+    assert rel_err(got, ref) <= TOL
+    top2 = np.sort(ref, -1)
+    clear = (top2[..., -1] - top2[..., -2]) > 1e-4 * np.abs(ref).max()
+    assert np.array_equal(got.argmax(-1)[clear], ref.argmax(-1)[clear])
+
+
+def test_state_dict_roundtrip_and_weight_refresh(golden):
+    from oracle import planner_oracle as po
+    g = golden("planner_K3.npz")
+    N, K = int(g["N"]), int(g["K"])
+    m = _model(_sd(g), N, K).eval()
+    x = torch.from_numpy(g["x"].astype(np.float32)).cuda()
+    S = torch.from_numpy(g["S"]).cuda()
+    m.addGSO(S)
+    with torch.no_grad():
+        a = torch.stack(m(x))
+        sd2 = po.init_state_dict(K, seed=3)
+        po.randomize_bn_stats(sd2, seed=4)
+        m.load_state_dict(sd2)                       # in-place copy_: the arena must be refreshed
+        b = torch.stack(m(x))
+        ref = torch.stack(po.planner_forward(sd2, S.cpu(), x.cpu()))
+    assert rel_err(b.cpu().numpy(), ref.numpy()) <= TOL
+    assert not torch.allclose(a, b)
+    assert sorted(m.state_dict().keys()) == sorted(_sd(g).keys())
+
+
+def test_api_asserts():
+    import gnn_pathplanning_b200 as gp
+    m = gp.DecentralPlannerNet(Cfg(4, 2)).cuda().eval()
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.rand(2, 1, 4, 4).cuda())      # decentralplanner.py:271 wants 3-D
+    m.addGSO(torch.rand(2, 4, 4).cuda())
+    with pytest.raises(RuntimeError):
+        m(torch.rand(2, 4, 3, 11, 11))                # CPU tensor: no fallback
