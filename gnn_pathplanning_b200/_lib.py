@@ -36,6 +36,7 @@ EXPORTED = (
     "gpp_graph_filter_backward_workspace_bytes", "gpp_graph_filter_backward",
     "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
     "gpp_planner_forward", "gpp_planner_forward_host",
+    "gpp_planner_set_profiling", "gpp_planner_get_profile",
     "gpp_launch_count", "gpp_reset_launch_count",
 )
 
@@ -115,6 +116,10 @@ def load():
         lib.gpp_planner_forward.argtypes = [vp, vp, vp, i, vp, vp, i, i, vp]
         lib.gpp_planner_forward_host.restype = i
         lib.gpp_planner_forward_host.argtypes = [vp, vp, vp, i, vp, i, i]
+        lib.gpp_planner_set_profiling.restype = i
+        lib.gpp_planner_set_profiling.argtypes = [vp, i]
+        lib.gpp_planner_get_profile.restype = i
+        lib.gpp_planner_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i)]
         lib.gpp_launch_count.restype = C.c_ulonglong
         lib.gpp_launch_count.argtypes = []
         lib.gpp_reset_launch_count.restype = None

@@ -16,6 +16,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 namespace gpp {
 
 // ---- error / bookkeeping ----------------------------------------------------------------
@@ -398,6 +400,10 @@ struct gpp_planner {
     size_t d_S_bytes;
     float* d_logits;
     size_t d_logits_floats;
+    // per-kernel event log (roofline report)
+    bool profiling;
+    std::vector<cudaEvent_t>* events;   // triples: start, after feature kernel, after filter kernel
+    size_t events_used;
 };
 
 extern "C" const char* gpp_last_error(void) { return gpp::g_err; }
@@ -463,7 +469,47 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->d_S);
     cudaFree(p->d_logits);
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->events) {
+        for (cudaEvent_t e : *p->events) cudaEventDestroy(e);
+        delete p->events;
+    }
     delete p;
+}
+
+extern "C" int gpp_planner_set_profiling(gpp_planner* p, int enable) {
+    GPP_REQUIRE(p, GPP_ERR_INVALID, "planner_set_profiling: null planner");
+    p->profiling = enable != 0;
+    if (enable && !p->events) p->events = new std::vector<cudaEvent_t>();
+    p->events_used = 0;
+    return GPP_OK;
+}
+
+extern "C" int gpp_planner_get_profile(gpp_planner* p, double* feature_ms, double* graph_filter_ms, int* steps) {
+    GPP_REQUIRE(p, GPP_ERR_INVALID, "planner_get_profile: null planner");
+    double fe = 0.0, gf = 0.0;
+    const size_t n = p->events_used / 3;
+    for (size_t i = 0; i < n; ++i) {
+        float a = 0.f, b = 0.f;
+        GPP_CUDA_OK(cudaEventSynchronize((*p->events)[3 * i + 2]));
+        GPP_CUDA_OK(cudaEventElapsedTime(&a, (*p->events)[3 * i], (*p->events)[3 * i + 1]));
+        GPP_CUDA_OK(cudaEventElapsedTime(&b, (*p->events)[3 * i + 1], (*p->events)[3 * i + 2]));
+        fe += a;
+        gf += b;
+    }
+    if (feature_ms) *feature_ms = fe;
+    if (graph_filter_ms) *graph_filter_ms = gf;
+    if (steps) *steps = (int)n;
+    p->events_used = 0;
+    return GPP_OK;
+}
+
+static cudaEvent_t next_event(gpp_planner* p) {
+    if (p->events_used == p->events->size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        p->events->push_back(e);
+    }
+    return (*p->events)[p->events_used++];
 }
 
 extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights* w, int on_device,
@@ -569,11 +615,22 @@ extern "C" int gpp_planner_forward(gpp_planner* p, const float* x, const void* S
     for (int l = 0; l < 5; ++l) { fa.sc[l] = A + p->off_sc[l]; fa.sh[l] = A + p->off_sh[l]; }
     fa.b5 = A + p->off_b5;
     const int grid = fa.num_tiles < sm_count() ? fa.num_tiles : sm_count();
+    const bool prof = p->profiling && p->events && p->events_used + 3 <= 3 * 8192;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (prof) {
+        e0 = next_event(p); e1 = next_event(p); e2 = next_event(p);
+        GPP_REQUIRE(e0 && e1 && e2, GPP_ERR_CUDA, "planner_forward: cudaEventCreate failed");
+        GPP_CUDA_OK(cudaEventRecord(e0, st));
+    }
     feature_kernel<<<grid, FE_THREADS, FE_SMEM_BYTES, st>>>(fa);
     GPP_LAUNCH_CHECK();
-    return launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
-                                  A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
-                                  GPP_NODE_MAJOR, 1, st);
+    if (prof) GPP_CUDA_OK(cudaEventRecord(e1, st));
+    int rc = launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
+                                    A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
+                                    GPP_NODE_MAJOR, 1, st);
+    if (rc) return rc;
+    if (prof) GPP_CUDA_OK(cudaEventRecord(e2, st));
+    return GPP_OK;
 }
 
 extern "C" int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,

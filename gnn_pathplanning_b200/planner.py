@@ -48,6 +48,29 @@ def weights_init(m):
         m.bias.data.fill_(0.0)
 
 
+class _Conv3x3Fp32(torch.autograd.Function):
+    """3x3 / stride 1 / pad 1 convolution pinned to true fp32 in BOTH directions: cuDNN would
+    otherwise run fp32 convolutions on TF32 tensor cores (2e-4 relative error, measured), which
+    breaks the 1e-5 parity bar.  The flag is read when the kernels run, so the backward needs
+    its own guard -- hence a Function rather than a context manager around the forward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            y = Fn.conv2d(x, w, b, stride=1, padding=1)
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            gx, gw, gb = torch.ops.aten.convolution_backward(
+                gy.contiguous(), x, w, [w.shape[0]], [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
+                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
+        return gx, gw, gb
+
+
 class _NativePlanner:
     """Owns one gpp_planner handle (per device) and keeps its weight arena in sync."""
 
@@ -228,7 +251,7 @@ class DecentralPlannerNet(nn.Module):
         h = x.reshape(B * N, 3, 11, 11).float()
         for l, ci in enumerate(_CONV_IDX):
             conv, bn = self.ConvLayers[ci], self.ConvLayers[ci + 1]
-            h = Fn.conv2d(h, conv.weight, conv.bias, stride=1, padding=1)
+            h = _Conv3x3Fp32.apply(h, conv.weight, conv.bias)
             h = Fn.relu(self._bn_per_agent(h, bn, N))
             if l % 2 == 0:
                 h = Fn.max_pool2d(h, 2)

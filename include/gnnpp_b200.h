@@ -144,6 +144,13 @@ int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_
 int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,
                              int s_is_f64, float* logits_host, int B, int N);
 
+/* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
+ * CUDA events before / between / after its two kernels on the launching stream (at most 8192
+ * steps are kept).  gpp_planner_get_profile synchronises on the recorded events, returns the
+ * summed durations in milliseconds and the number of steps they cover, and clears the log. */
+int gpp_planner_set_profiling(gpp_planner* p, int enable);
+int gpp_planner_get_profile(gpp_planner* p, double* feature_ms, double* graph_filter_ms, int* steps);
+
 /* Number of kernels of this library launched by the calling thread's planner calls since
  * the last reset (bench.py's gpu_launches claim is read from here, not guessed). */
 unsigned long long gpp_launch_count(void);
