@@ -91,13 +91,13 @@ def graph_filter(x, S, weight, bias=None, fuse_relu=False, x_layout=FEATURE_MAJO
     x [B,G,N] (feature-major, the reference layout) or [B,N,G] (node-major); S [B,N,N]
     or [B,1,N,N], f32 or f64; weight [F,1,K,G]; bias [F,1] or None.  Differentiable in
     x, weight and bias (S gets no gradient, as in the reference)."""
-    _require_cuda(x, "x")
-    _require_cuda(S, "S")
-    _require_cuda(weight, "weight")
     if weight.shape[1] != 1:
         raise NotImplementedError(
             "gnn_pathplanning_b200: E=%d edge features; the planner path only ever builds E=1 "
             "(decentralplanner.py:209)" % weight.shape[1])
+    _require_cuda(x, "x")
+    _require_cuda(S, "S")
+    _require_cuda(weight, "weight")
     if x.dtype != torch.float32 or weight.dtype != torch.float32:
         raise TypeError("gnn_pathplanning_b200: x and weight must be float32")
     return _GraphFilterFn.apply(x, _gso3(S), weight, bias, bool(fuse_relu), x_layout, y_layout)

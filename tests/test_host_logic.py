@@ -1,0 +1,133 @@
+"""CPU: host-side logic -- the C-ABI library loads and exports every declared symbol, the
+drop-in modules keep the reference's API surface, the product never imports the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, rel_err
+
+
+class Cfg:
+    def __init__(self, n, k):
+        self.num_agents, self.nGraphFilterTaps, self.device = n, k, "cpu"
+
+
+def test_library_exports_every_declared_symbol():
+    from gnn_pathplanning_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "gnnpp_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(gpp_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()           # loads without a GPU (no compute calls here)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.EXPORTED) == declared
+    assert lib.gpp_abi_version() == 1
+
+
+def test_state_dict_surface_and_init_match_reference(golden):
+    import gnn_pathplanning_b200 as gp
+    for f, K in (("planner_K3.npz", 3), ("planner_K2.npz", 2)):
+        g = golden(f)
+        torch.manual_seed(1337)
+        m = gp.DecentralPlannerNet(Cfg(10, K))
+        sd = m.state_dict()
+        keys = sorted(sd.keys())
+        assert keys == [str(k) for k in g["init_keys"]]
+        for k in keys:
+            assert tuple(sd[k].shape) == tuple(g["sd_" + k].shape), k
+        fp = np.array([float(sd[k].double().sum()) for k in keys])
+        assert np.allclose(fp, g["init_fingerprint"], rtol=0, atol=1e-9)     # same init as the reference
+        assert (m.numAgents, m.numFeatures2Share, m.L, m.F, m.K, m.E, m.bias) == (10, 128, 1, [128, 128], [K], 1, True)
+        names = [n for n, _ in m.named_parameters()]
+        assert any(n.startswith("GFL.") for n in names) and any(n.startswith("actionsMLP.") for n in names)
+
+
+def test_graph_filter_module_surface():
+    import gnn_pathplanning_b200 as gp
+    lay = gp.GraphFilterBatch(6, 10, 3)
+    assert tuple(lay.weight.shape) == (10, 1, 3, 6) and tuple(lay.bias.shape) == (10, 1)
+    bound = 1.0 / np.sqrt(6 * 3)
+    assert float(lay.weight.detach().abs().max()) <= bound and float(lay.bias.detach().abs().max()) <= bound
+    assert gp.GraphFilterBatch(6, 10, 3, bias=False).bias is None
+    assert "no GSO stored" in lay.extra_repr()
+    with pytest.raises(AssertionError):
+        lay.addGSO(torch.rand(2, 5, 5))
+    lay.addGSO(torch.rand(2, 1, 5, 5))
+    assert "GSO stored" in lay.extra_repr() and lay.N == 5
+    with pytest.raises(RuntimeError, match="does not fall back"):
+        lay(torch.rand(2, 6, 5))                         # CPU tensors: loud failure, no fallback
+    with pytest.raises(NotImplementedError):                 # E != 1 is outside the planner path
+        gp.graph_filter(torch.rand(1, 6, 5), torch.rand(1, 2, 5, 5), torch.rand(10, 2, 3, 6))
+
+
+def test_planner_api_asserts_on_cpu():
+    import gnn_pathplanning_b200 as gp
+    m = gp.DecentralPlannerNet(Cfg(4, 2))
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.rand(2, 1, 4, 4))
+    m.addGSO(torch.rand(2, 4, 4))
+    assert tuple(m.S.shape) == (2, 1, 4, 4)
+    with pytest.raises(RuntimeError, match="does not fall back"):
+        m(torch.rand(2, 4, 3, 11, 11))
+
+
+def test_per_agent_batchnorm_matches_reference_semantics():
+    """The batched CNN pass must reproduce the reference's per-agent BatchNorm statistics and
+    its N sequential running-stat updates (decentralplanner.py:284-286)."""
+    import gnn_pathplanning_b200 as gp
+    from gnn_pathplanning_b200 import planner as pl
+    from oracle import planner_oracle as po
+    N, K, B = 3, 2, 4
+    sd = po.init_state_dict(K, seed=1)
+    po.randomize_bn_stats(sd)
+    m = gp.DecentralPlannerNet(Cfg(N, K))
+    m.load_state_dict(sd)
+    m.train()
+    x = (torch.rand(B, N, 3, 11, 11, generator=torch.Generator().manual_seed(0)) > 0.6).float()
+    h = x.reshape(B * N, 3, 11, 11)
+    for l, ci in enumerate(pl._CONV_IDX):
+        conv, bn = m.ConvLayers[ci], m.ConvLayers[ci + 1]
+        h = pl._Conv3x3Fp32.apply(h, conv.weight, conv.bias)
+        h = torch.relu(m._bn_per_agent(h, bn, N))
+        if l % 2 == 0:
+            h = torch.nn.functional.max_pool2d(h, 2)
+    feat = h.reshape(B, N, 128)
+    bn_state = {k: v.clone() for k, v in sd.items() if "running" in k or "tracked" in k}
+    ref = torch.stack([po._cnn_one_agent(sd, x[:, i], True, bn_state).reshape(B, 128) for i in range(N)], 1)
+    assert rel_err(feat.detach().numpy(), ref.numpy()) <= 1e-6
+    after = m.state_dict()
+    for k, v in bn_state.items():
+        assert rel_err(after[k].double().numpy(), v.double().numpy()) <= 1e-6, k
+
+
+def test_dropin_names_resolve():
+    import gnn_pathplanning_b200 as gp
+    import sys
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("graphs", "utils")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        gp.install_dropin()
+        from graphs.models.decentralplanner import DecentralPlannerNet
+        from graphs.weights_initializer import weights_init
+        import utils.graphUtils.graphML as gml
+        assert DecentralPlannerNet is gp.DecentralPlannerNet
+        assert gml.GraphFilterBatch is gp.GraphFilterBatch and gml.BatchLSIGF is gp.BatchLSIGF
+        assert weights_init is gp.weights_init
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("graphs", "utils")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gnn_pathplanning_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "planner_oracle" not in src and "ref_shim" not in src, f
