@@ -14,8 +14,8 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgnnpp_b200.so")
-SOURCES = ("graph_filter.cu", "planner.cu")
-HEADERS = ("common.cuh",)
+SOURCES = ("graph_filter.cu", "feature.cu", "planner.cu")
+HEADERS = ("common.cuh", "feature.cuh")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200.h")
 
 NVCC_FLAGS = [

@@ -32,11 +32,11 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, in
                                               const float* __restrict__ wm, int n_out,
                                               float* __restrict__ out_s, int OS, int part_stride,
                                               int RP, int nks) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int n_cg = n_out >> 5, n_rt = RP >> 4;
     const int n_items = n_cg * n_rt * nks;
     const int len = n_in / nks;
-    for (int item = warp; item < n_items; item += GF_WARPS) {
+    for (int item = warp; item < n_items; item += nwarps) {
         const int cg = item % n_cg;
         const int rt = (item / n_cg) % n_rt;
         const int ks = item / (n_cg * n_rt);
@@ -84,10 +84,10 @@ __device__ __forceinline__ void load_gso_plain(float* Ss, const void* S, int s_i
                                                int count) {
     if (s_is_f64) {
         const double* Sd = reinterpret_cast<const double*>(S) + off;
-        for (int i = threadIdx.x; i < count; i += GF_THREADS) Ss[i] = static_cast<float>(Sd[i]);
+        for (int i = threadIdx.x; i < count; i += blockDim.x) Ss[i] = static_cast<float>(Sd[i]);
     } else {
         const float* Sf = reinterpret_cast<const float*>(S) + off;
-        for (int i = threadIdx.x; i < count; i += GF_THREADS) Ss[i] = Sf[i];
+        for (int i = threadIdx.x; i < count; i += blockDim.x) Ss[i] = Sf[i];
     }
 }
 
@@ -110,7 +110,9 @@ struct GfFwdSmem {
     __host__ __device__ GfFwdSmem(int N, int K, int TS) {
         RP = ((TS * N + 15) / 16) * 16;
         ZS = K * GF_C + 4;
-        nks = ((RP / 16) & 1) ? 2 : 1;
+        // split the K*G reduction so that the 4 column groups x row tiles x splits fill 16 warps
+        const int n_rt = RP / 16;
+        nks = (n_rt >= 4 && (n_rt & 3) == 0) ? 1 : ((n_rt & 1) ? 4 : 2);
         s_floats = ((TS * N * N + 3) / 4) * 4;
     }
     __host__ __device__ size_t z_off() const { return 16; }
@@ -124,7 +126,10 @@ struct GfFwdSmem {
     }
 };
 
-__global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
+constexpr int GF_FWD_THREADS = 512;
+constexpr int GF_FWD_WARPS = GF_FWD_THREADS / 32;
+
+__global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GfFwdSmem L(a.N, a.K, a.TS);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -141,9 +146,9 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
         mbar_init(bar, 1);
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < GF_C; i += GF_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < GF_C; i += GF_FWD_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
     if (a.wa) {
-        for (int i = threadIdx.x; i < NUM_ACT * GF_C; i += GF_THREADS) wa_s[i] = a.wa[i];
+        for (int i = threadIdx.x; i < NUM_ACT * GF_C; i += GF_FWD_THREADS) wa_s[i] = a.wa[i];
         if (threadIdx.x < NUM_ACT) ba_s[threadIdx.x] = a.ba[threadIdx.x];
     }
     __syncthreads();
@@ -179,14 +184,14 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
         if (!a.bulk_x) {
             if (a.x_layout == GPP_NODE_MAJOR) {
                 const float4* xp = reinterpret_cast<const float4*>(a.x + row0 * GF_C);
-                for (int i = threadIdx.x; i < R * (GF_C / 4); i += GF_THREADS) {
+                for (int i = threadIdx.x; i < R * (GF_C / 4); i += GF_FWD_THREADS) {
                     const int r = i >> 5, q = i & 31;
                     *reinterpret_cast<float4*>(z + r * ZS + q * 4) = xp[i];
                 }
             } else {  // [B, G, N]: contiguous per sample, transposed into node-major rows
                 const float* xp = a.x + (size_t)s0 * GF_C * N;
                 const int per = GF_C * N;
-                for (int i = threadIdx.x; i < ns * per; i += GF_THREADS) {
+                for (int i = threadIdx.x; i < ns * per; i += GF_FWD_THREADS) {
                     const int bl = i / per, rem = i - bl * per;
                     const int g = rem / N, n = rem - g * N;
                     z[(bl * N + n) * ZS + g] = xp[i];
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
             }
         }
         // zero the padding rows of the k = 0 slot (the other slots are produced below)
-        for (int i = threadIdx.x; i < (RP - R) * GF_C; i += GF_THREADS)
+        for (int i = threadIdx.x; i < (RP - R) * GF_C; i += GF_FWD_THREADS)
             z[(R + i / GF_C) * ZS + (i % GF_C)] = 0.f;
         if (a.bulk_x || a.bulk_s) {
             mbar_wait(bar, phase);
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
 
         // ---- 2. propagate: z_k[n,:] = sum_m S[m,n] z_{k-1}[m,:]  (x.S of graphML.py:2350) ---
         for (int k = 1; k < K; ++k) {
-            for (int r = warp; r < RP; r += GF_WARPS) {
+            for (int r = warp; r < RP; r += GF_FWD_WARPS) {
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < R) {
                     const int bl = r / N, n = r - bl * N;
@@ -230,10 +235,10 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
         __syncthreads();
 
         // ---- 4. epilogue: bias, ReLU, y store, fused action MLP -------------------------
-        for (int i = threadIdx.x; i < R * GF_C; i += GF_THREADS) {
+        for (int i = threadIdx.x; i < R * GF_C; i += GF_FWD_THREADS) {
             const int r = i >> 7, f = i & 127;
             float v = part[r * GF_PS + f];
-            if (nks == 2) v += part[L.RP * GF_PS + r * GF_PS + f];
+            for (int ks = 1; ks < nks; ++ks) v += part[ks * L.RP * GF_PS + r * GF_PS + f];
             v += bias_s[f];
             if (a.relu) v = fmaxf(v, 0.f);
             part[r * GF_PS + f] = v;
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
         if (a.y && a.y_layout == GPP_FEATURE_MAJOR) {
             float* yp = a.y + (size_t)s0 * GF_C * N;
             const int per = GF_C * N;
-            for (int i = threadIdx.x; i < ns * per; i += GF_THREADS) {
+            for (int i = threadIdx.x; i < ns * per; i += GF_FWD_THREADS) {
                 const int bl = i / per, rem = i - bl * per;
                 const int f = rem / N, n = rem - f * N;
                 yp[i] = part[(bl * N + n) * GF_PS + f];
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(GF_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
         if (a.wa) {
             // logits[n][b][:] = wa . y[b,n,:] + ba   (decentralplanner.py:309-315); one warp
             // per node row, 4 features per lane, butterfly reduction across the warp
-            for (int r = warp; r < R; r += GF_WARPS) {
+            for (int r = warp; r < R; r += GF_FWD_WARPS) {
                 const float4 v = ld_smem4(part + r * GF_PS + lane * 4);
                 float s[NUM_ACT];
 #pragma unroll
@@ -685,15 +690,15 @@ int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t
 int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const float* wt,
                            const float* bias, float* y, const float* wa, const float* ba,
                            float* logits, int B, int N, int K, int x_layout, int y_layout,
-                           int relu, cudaStream_t st) {
+                           int relu, int allow_bulk, cudaStream_t st) {
     GfFwdArgs a;
     a.x = x; a.S = S; a.wt = wt; a.bias = bias; a.y = y; a.wa = wa; a.ba = ba; a.logits = logits;
     a.B = B; a.N = N; a.K = K;
     a.TS = pick_tile_samples(B, N);
     a.num_tiles = (B + a.TS - 1) / a.TS;
     a.s_is_f64 = s_is_f64; a.x_layout = x_layout; a.y_layout = y_layout; a.relu = relu;
-    a.bulk_x = (x_layout == GPP_NODE_MAJOR && aligned16(x)) ? 1 : 0;
-    a.bulk_s = (!s_is_f64 && aligned16(S) && ((N * N) % 4 == 0)) ? 1 : 0;
+    a.bulk_x = (allow_bulk && x_layout == GPP_NODE_MAJOR && aligned16(x)) ? 1 : 0;
+    a.bulk_s = (allow_bulk && !s_is_f64 && aligned16(S) && ((N * N) % 4 == 0)) ? 1 : 0;
     const GfFwdSmem L(N, K, a.TS);
     const size_t smem = L.total();
     static size_t configured = 0;
@@ -706,7 +711,7 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     int grid = a.num_tiles < sm_count() * per_sm ? a.num_tiles : sm_count() * per_sm;
-    gf_fwd_kernel<<<grid, GF_THREADS, smem, st>>>(a);
+    gf_fwd_kernel<<<grid, GF_FWD_THREADS, smem, st>>>(a);
     GPP_LAUNCH_CHECK();
     return GPP_OK;
 }
@@ -737,7 +742,7 @@ extern "C" int gpp_graph_filter_forward(const float* x, const void* S, int s_is_
         int rc = launch_transpose_taps(w, wt, F, K * G, st);
         if (rc) return rc;
         return launch_gf_forward_fast(x, S, s_is_f64, wt, bias, y, nullptr, nullptr, nullptr, B, N, K,
-                                      x_layout, y_layout, fuse_relu, st);
+                                      x_layout, y_layout, fuse_relu, 1, st);
     }
     const size_t smem = generic_fwd_smem(N, G, K);
     GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED,

@@ -148,8 +148,17 @@ class DecentralPlannerNet(nn.Module):
 
     # ------------------------------------------------------- fused inference
     def _weights_key(self):
-        ts = [p for p in self.parameters()] + [b for b in self.buffers()]
-        return tuple((t.data_ptr(), t._version) for t in ts)
+        # (storage address, in-place version counter) of every parameter / buffer: changes on
+        # optimizer steps, load_state_dict (copy_), .to()/.cuda() (new storage) and BN updates
+        ts = self.__dict__.get("_key_tensors")
+        if ts is None:
+            ts = [p for p in self.parameters()] + [b for b in self.buffers()]
+            self.__dict__["_key_tensors"] = ts
+        return tuple([t._version for t in ts] + [ts[0].data_ptr(), ts[-1].data_ptr()])
+
+    def _apply(self, fn, *a, **k):
+        self.__dict__["_key_tensors"] = None          # .to()/.cuda() may replace parameter objects
+        return super()._apply(fn, *a, **k)
 
     def _native_for(self, device) -> _NativePlanner:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -180,6 +189,7 @@ class DecentralPlannerNet(nn.Module):
             _lib.check(nat.lib.gpp_planner_set_weights(
                 nat.handle, C.byref(w), 1, torch.cuda.current_stream().cuda_stream))
             nat.key = key
+            nat.fresh = True
         return nat
 
     def _forward_fused(self, x, S):
@@ -210,7 +220,9 @@ class DecentralPlannerNet(nn.Module):
         B, N = x_host.shape[0], x_host.shape[1]
         dev = torch.device(device) if device is not None else next(self.parameters()).device
         nat = self._native_for(dev)
-        torch.cuda.current_stream(dev).synchronize()      # weight re-layout (if any) is done
+        if getattr(nat, "fresh", False):                  # weight re-layout ran on torch's stream:
+            torch.cuda.current_stream(dev).synchronize()  # finish it before the planner's own stream
+            nat.fresh = False
         if out_host is None:
             out_host = torch.empty(N, B, 5, dtype=torch.float32).pin_memory()
         assert S_host.dtype in (torch.float32, torch.float64)
