@@ -43,6 +43,13 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
                            const float* bias, float* y, const float* wa, const float* ba,
                            float* logits, int B, int N, int K, int x_layout, int y_layout,
                            int relu, int allow_bulk, cudaStream_t st);
+// tensor-core path (graph_filter_tc.cu)
+size_t gf_tc_image_floats(int K);
+int gf_tc_tile_samples(int N, int K);
+int launch_prep_umma_taps(const float* w, float* img, int K, cudaStream_t st);
+int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const float* wimg, const float* bias,
+                         float* y, const float* wa, const float* ba, float* logits, int B, int N, int K,
+                         int relu, int allow_bulk, cudaStream_t st);
 
 // scale = gamma / sqrt(var + eps);  shift = (conv_bias - mean) * scale + beta
 __global__ void fold_bn_kernel(const float* conv_b, const float* g, const float* b, const float* mean,
@@ -66,7 +73,8 @@ struct gpp_planner {
     float* arena;        // prepared weights
     size_t off_w[6];     // conv0..4 k-major, compress k-major
     size_t off_sc[5], off_sh[5];
-    size_t off_b5, off_gfw, off_gfb, off_wa, off_ba, arena_floats;
+    size_t off_b5, off_gfw, off_gfb, off_wa, off_ba, off_gfimg, arena_floats;
+    int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
     bool weights_set;
     float* raw;          // device staging for host-provided parameters
     size_t raw_floats;
@@ -123,6 +131,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     p->off_gfb = take(128);
     p->off_wa = take(5 * 128);
     p->off_ba = take(64);
+    p->off_gfimg = take(gf_tc_image_floats(K));      // pre-split, pre-swizzled tcgen05 B-operand chunks
     p->arena_floats = off;
     if (cudaMalloc(&p->arena, sizeof(float) * off) != cudaSuccess) {
         set_error("planner_create: cudaMalloc(%zu) failed", sizeof(float) * off);
@@ -153,6 +162,12 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
         delete p->events;
     }
     delete p;
+}
+
+extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
+    GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_graph_filter_mode: mode must be 0, 1 or 2");
+    p->gf_mode = mode;
+    return GPP_OK;
 }
 
 extern "C" int gpp_planner_set_profiling(gpp_planner* p, int enable) {
@@ -245,6 +260,8 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     if (rc) return rc;
     rc = launch_transpose_taps(d.gf_w, A + p->off_gfw, 128, K * 128, st);
     if (rc) return rc;
+    rc = launch_prep_umma_taps(d.gf_w, A + p->off_gfimg, K, st);
+    if (rc) return rc;
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_b5, d.compress_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_gfb, d.gf_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_wa, d.action_w, sizeof(float) * 5 * 128, cudaMemcpyDeviceToDevice, st));
@@ -295,9 +312,17 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     int rc = launch_feature_kernel(fa, st);
     if (rc) return rc;
     if (prof) GPP_CUDA_OK(cudaEventRecord(e1, st));
-    rc = launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
-                                A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
-                                GPP_NODE_MAJOR, 1, allow_bulk, st);
+    const bool tc_fits = gf_tc_tile_samples(N, p->K) > 0;
+    GPP_REQUIRE(p->gf_mode != 2 || tc_fits, GPP_ERR_UNSUPPORTED,
+                "planner_forward: tensor-core graph filter requested but N=%d K=%d does not fit its tile", N, p->K);
+    const bool use_tc = tc_fits && (p->gf_mode == 2 || (p->gf_mode == 0 && rows >= 4096));
+    if (use_tc)
+        rc = launch_gf_forward_tc(feat, S, s_is_f64, A + p->off_gfimg, A + p->off_gfb, nullptr, A + p->off_wa,
+                                  A + p->off_ba, logits, B, N, p->K, 1, allow_bulk, st);
+    else
+        rc = launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
+                                    A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
+                                    GPP_NODE_MAJOR, 1, allow_bulk, st);
     if (rc) return rc;
     if (prof) GPP_CUDA_OK(cudaEventRecord(e2, st));
     return GPP_OK;

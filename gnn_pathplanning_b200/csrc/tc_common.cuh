@@ -1,0 +1,105 @@
+// tcgen05 / TMEM helpers (sm_100a inline PTX) shared by the tensor-core kernels.
+//
+// Operand convention used throughout: K-major tiles in the canonical SWIZZLE_128B shared-memory
+// layout -- rows of 128 bytes (32 tf32 values = one K chunk), 8-row groups of 1024 bytes, and
+// inside each row the 16-byte chunk j is stored at position j ^ (row & 7).  Tile bases are
+// 1024-byte aligned.  One tcgen05.mma.kind::tf32 consumes K = 8 (32 bytes): the descriptor's start
+// address advances by 32 bytes per K step inside the 128-byte swizzle atom.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpp {
+
+// byte offset of (row, 16-byte chunk j) inside a SWIZZLE_128B K-major tile
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int j) {
+    return (uint32_t)(((row >> 3) << 10) + ((row & 7) << 7) + (((j ^ row) & 7) << 4));
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in bits [0,14),
+// leading byte offset >> 4 in [16,30) (=1, unused for swizzled K-major), stride byte offset >> 4 in
+// [32,46) (1024 B between 8-row groups), version 1 in [46,48), layout type SWIZZLE_128B (=2) in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, A and B
+// K-major: c_format F32 (1) at [4,6), a/b format TF32 (2) at [7,10)/[10,13), N>>3 at [17,23),
+// M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// Arrives on the mbarrier once every tcgen05 operation issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// TMEM allocation: one full warp; the base address is written to *slot (shared memory).
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives lane (base lane + i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 -> (hi, lo) with hi = tf32(x) (round to nearest), lo = tf32(x - hi): x = hi + lo up to 2^-22 |x|
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    const float rem = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rem));
+    lo = __uint_as_float(l);
+}
+
+}  // namespace gpp

@@ -80,6 +80,7 @@ class _NativePlanner:
         _lib.check(self.lib.gpp_planner_create(C.byref(h), K))
         self.handle = h
         self.key = None
+        self.gf_mode = None
 
     def __del__(self):
         try:
@@ -190,7 +191,15 @@ class DecentralPlannerNet(nn.Module):
                 nat.handle, C.byref(w), 1, torch.cuda.current_stream().cuda_stream))
             nat.key = key
             nat.fresh = True
+        mode = self.__dict__.get("_gf_mode", 0)
+        if nat.gf_mode != mode:
+            _lib.check(nat.lib.gpp_planner_set_graph_filter_mode(nat.handle, mode))
+            nat.gf_mode = mode
         return nat
+
+    def set_graph_filter_mode(self, mode: str) -> None:
+        """'auto' (default), 'cuda' (fp32 CUDA-core kernel) or 'tc' (tcgen05 3xTF32 kernel)."""
+        self.__dict__["_gf_mode"] = {"auto": 0, "cuda": 1, "tc": 2}[mode]
 
     def _forward_fused(self, x, S):
         B, N = x.shape[0], x.shape[1]

@@ -144,6 +144,15 @@ int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_
 int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,
                              int s_is_f64, float* logits_host, int B, int N);
 
+/* Which graph-filter kernel the planner uses: 0 = automatic (tensor cores once B*N >= 4096 node
+ * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 3xTF32 kernel (gf_fwd_tc_kernel;
+ * GPP_ERR_UNSUPPORTED at forward time if N/K do not fit its 128-row tile). */
+int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode);
+
+/* Test hook for the tcgen05 plumbing: D[128][128] = A[128][32] . B[128][32]^T on the tensor cores
+ * (A, B tf32-representable fp32, row-major, device memory). */
+int gpp_debug_umma_selftest(const float* A, const float* B, float* D, void* stream);
+
 /* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
  * CUDA events before / between / after its two kernels on the launching stream (at most 8192
  * steps are kept).  gpp_planner_get_profile synchronises on the recorded events, returns the
