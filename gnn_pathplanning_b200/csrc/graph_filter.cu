@@ -13,6 +13,8 @@
 // fp32 FMA throughout: the result is within a few ulp of the reference's f32 matmuls.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace gpp {
 
 constexpr int GF_THREADS = 256;
@@ -718,10 +720,31 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
 
 }  // namespace gpp
 
+namespace gpp {
+// tensor-core path (graph_filter_tc.cu)
+size_t gf_tc_image_floats(int K);
+int gf_tc_tile_samples(int N, int K);
+int launch_prep_umma_taps(const float* w, float* img, int K, cudaStream_t st);
+int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const float* wimg, const float* bias,
+                         float* y, const float* wa, const float* ba, float* logits, int B, int N, int K,
+                         int relu, int allow_bulk, cudaStream_t st);
+
+// GPP_GF_MODE environment override for the standalone op: 0 auto, 1 CUDA-core, 2 tensor-core
+static int standalone_gf_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("GPP_GF_MODE");
+        mode = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 0;
+    }
+    return mode;
+}
+}  // namespace gpp
+
 using namespace gpp;
 
 extern "C" size_t gpp_graph_filter_workspace_bytes(int G, int F, int K) {
-    if (G == GF_C && F == GF_C) return sizeof(float) * (size_t)K * G * F;
+    // k-major transposed taps (CUDA-core kernel) or split/swizzled chunk images (tensor-core kernel)
+    if (G == GF_C && F == GF_C) return sizeof(float) * gf_tc_image_floats(K);
     return 0;
 }
 
@@ -738,6 +761,14 @@ extern "C" int gpp_graph_filter_forward(const float* x, const void* S, int s_is_
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (G == GF_C && F == GF_C && N <= GF_MAX_ROWS) {
         GPP_REQUIRE(workspace, GPP_ERR_INVALID, "graph_filter_forward: workspace required");
+        const int mode = standalone_gf_mode();
+        if (x_layout == GPP_NODE_MAJOR && y_layout == GPP_NODE_MAJOR && mode != 1 && gf_tc_tile_samples(N, K) > 0 &&
+            (mode == 2 || (size_t)B * N >= 4096)) {
+            float* img = reinterpret_cast<float*>(workspace);
+            int rc = launch_prep_umma_taps(w, img, K, st);
+            if (rc) return rc;
+            return launch_gf_forward_tc(x, S, s_is_f64, img, bias, y, nullptr, nullptr, nullptr, B, N, K, fuse_relu, 1, st);
+        }
         float* wt = reinterpret_cast<float*>(workspace);
         int rc = launch_transpose_taps(w, wt, F, K * G, st);
         if (rc) return rc;

@@ -13,9 +13,11 @@
 //   * A operand (node signals): CUDA cores build each 128 x 32 chunk of z_k = (S^k)^T x straight from the
 //     fp32 x tile and the per-sample GSO powers in shared memory, split it and store it swizzled;
 //     a 2-stage ring overlaps this with the MMAs of the previous chunk (tcgen05.commit -> mbarrier).
-//   * accumulator: 128 lanes x 128 fp32 columns of TMEM; the epilogue reads it with tcgen05.ld
-//     (one thread per node row), adds bias, applies ReLU, optionally stores y and reduces the action
-//     logits in-thread.
+//   * accumulators: 4 x (128 lanes x 128 fp32 columns) = all 512 TMEM columns, used round-robin by K
+//     chunk so that each one sees a quarter of the accumulation steps (the tensor core's fp32
+//     accumulation is not round-to-nearest; measured 4e-6 relative error with a single accumulator).
+//     The epilogue reads them with tcgen05.ld (one thread per node row), sums them in fp32, adds
+//     bias, applies ReLU, optionally stores y and reduces the action logits in-thread.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -30,6 +32,8 @@ constexpr int TC_OP_BYTES = TC_M * 128;    // one operand half (hi or lo) of one
 constexpr int TC_STAGE_BYTES = 4 * TC_OP_BYTES;   // A_hi | A_lo | B_hi | B_lo
 constexpr int TC_ACT = 5;
 constexpr uint32_t TC_IDESC = umma_idesc_tf32(TC_M, TC_C);
+constexpr int TC_NACC = 4;                 // TMEM accumulators (128 columns each)
+constexpr int TC_TMEM_COLS = TC_NACC * TC_C;
 
 // ---------------------------------------------------------------------------------------
 // B-operand images: img[chunk] = { hi[128 x 32] , lo[128 x 32] } in SWIZZLE_128B K-major layout,
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gf_fwd_tc_kernel(const GfTcArgs
         mbar_init(xbar, 1);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc<TC_C>(tmem_slot);
+    if (warp == 0) tmem_alloc<TC_TMEM_COLS>(tmem_slot);
     for (int i = tid; i < TC_C; i += TC_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
     if (a.wa) {
         for (int i = tid; i < TC_ACT * TC_C; i += TC_THREADS) wa_s[i] = a.wa[i];
@@ -213,15 +217,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gf_fwd_tc_kernel(const GfTcArgs
                 const uint32_t sa = smem_u32(stage);
                 const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + TC_OP_BYTES);
                 const uint64_t b_hi = umma_desc_sw128(sa + 2 * TC_OP_BYTES), b_lo = umma_desc_sw128(sa + 3 * TC_OP_BYTES);
+                const uint32_t acc = tmem_acc + (uint32_t)(c % TC_NACC) * TC_C;   // round-robin accumulator
+                const uint32_t fresh = (c < TC_NACC) ? 0u : 1u;                  // first chunk into it overwrites
 #pragma unroll
                 for (int ks = 0; ks < TC_CHUNK_K / 8; ++ks)     // +32 bytes (2 x 16 B units) per K = 8 step
-                    umma_tf32(tmem_acc, a_hi + 2 * ks, b_hi + 2 * ks, TC_IDESC, (c | ks) != 0);
+                    umma_tf32(acc, a_hi + 2 * ks, b_hi + 2 * ks, TC_IDESC, (ks != 0) ? 1u : fresh);
 #pragma unroll
                 for (int ks = 0; ks < TC_CHUNK_K / 8; ++ks)
-                    umma_tf32(tmem_acc, a_lo + 2 * ks, b_hi + 2 * ks, TC_IDESC, 1u);
+                    umma_tf32(acc, a_lo + 2 * ks, b_hi + 2 * ks, TC_IDESC, 1u);
 #pragma unroll
                 for (int ks = 0; ks < TC_CHUNK_K / 8; ++ks)
-                    umma_tf32(tmem_acc, a_hi + 2 * ks, b_lo + 2 * ks, TC_IDESC, 1u);
+                    umma_tf32(acc, a_hi + 2 * ks, b_lo + 2 * ks, TC_IDESC, 1u);
                 umma_commit(&done[st]);
             }
         }
@@ -240,6 +246,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gf_fwd_tc_kernel(const GfTcArgs
                 for (int cb = 0; cb < TC_C / 32; ++cb) {
                     float v[32];
                     tmem_ld_32x32(tmem_acc + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+                    const int nacc = nchunks < TC_NACC ? nchunks : TC_NACC;
+                    for (int q = 1; q < nacc; ++q) {
+                        float u[32];
+                        tmem_ld_32x32(tmem_acc + ((uint32_t)(warp * 32) << 16) + q * TC_C + cb * 32, u);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] += u[i];
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         float t = v[i] + bias_s[cb * 32 + i];
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gf_fwd_tc_kernel(const GfTcArgs
             tcgen05_fence_after();
         }
     }
-    if (warp == 0) tmem_dealloc<TC_C>(tmem_acc);
+    if (warp == 0) tmem_dealloc<TC_TMEM_COLS>(tmem_acc);
 }
 
 // ---------------------------------------------------------------------------------------
