@@ -192,6 +192,37 @@ def time_cpu(step, budget_s, min_steps=5, warmup=3):
     return n, el
 
 
+def saturated_filter_roofline(gp, dev, batch, hbm_peak, peak_src):
+    """The fused graph filter alone (node-major in/out, + ReLU) on a batch large enough to fill the
+    machine: the headline configuration moves only 0.68 MB per launch and is launch-latency bound, so
+    this is where the kernel's bandwidth fraction is visible.  Inputs (batch x 10 x 128 floats and
+    the GSOs) exceed L2; CUDA events around back-to-back launches; the ~3 us tap re-layout launch
+    that precedes every standalone call is inside the timed region."""
+    g = torch.Generator().manual_seed(0)
+    w = ((torch.rand(128, 1, K_TAPS, 128, generator=g) - 0.5) * 0.2).to(dev)
+    b = (torch.rand(128, 1, generator=g) - 0.5).to(dev)
+    x = torch.randn(batch, N_AGENTS, 128, device=dev)
+    S = torch.rand(batch, N_AGENTS, N_AGENTS, device=dev) * 0.2
+    for _ in range(3):
+        gp.graph_filter(x, S, w, b, True, gp.NODE_MAJOR, gp.NODE_MAJOR)
+    torch.cuda.synchronize()
+    iters = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        gp.graph_filter(x, S, w, b, True, gp.NODE_MAJOR, gp.NODE_MAJOR)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / iters
+    nbytes = GF_BYTES_PER_AGENT_STEP * batch * N_AGENTS
+    gbs = nbytes / sec / 1e9
+    return {"kernel": "gf_fwd_tc_kernel (tcgen05 3xTF32, TMEM accumulators) via gpp_graph_filter_forward",
+            "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            "traffic": None, "peak_source": peak_src, "mean_launch_us": sec * 1e6,
+            "workload": "K=3, 10 agents, %d episodes (%.0f MB of node signals + GSOs, > L2)" % (batch, nbytes / 2e6),
+            "agent_steps_per_s": batch * N_AGENTS / sec, "algorithmic_bytes_per_launch": nbytes}
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's own CPU implementation of the path = its PyTorch-CPU op
     sequence, restated in oracle/planner_oracle.py (the Python reference cannot travel to the
@@ -243,6 +274,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--pool-mb", type=float, default=160.0, help="device input pool size (> L2)")
+    ap.add_argument("--gf-mode", default="auto", choices=["auto", "cuda", "tc"],
+                    help="graph-filter kernel of the planner: auto / CUDA-core / tcgen05")
+    ap.add_argument("--sat-batch", type=int, default=32768,
+                    help="episodes in the saturated graph-filter roofline measurement (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -274,6 +309,7 @@ def main():
     model = gp.DecentralPlannerNet(Cfg())
     model.load_state_dict(sd)
     model = model.to(dev).eval()
+    model.set_graph_filter_mode(args.gf_mode)
 
     # ---- inputs: a few unique synthetic batches, replicated (sample-permuted) into a pool > L2
     unique = 8
@@ -385,6 +421,8 @@ def main():
                                       "algorithmic_bytes_per_launch": GF_BYTES_PER_AGENT_STEP * agent_steps,
                                       "algorithmic_flops_per_launch": GF_FLOPS_PER_AGENT_STEP * agent_steps},
         }
+        if args.sat_batch > 0:
+            line["roofline_graph_filter_saturated"] = saturated_filter_roofline(gp, dev, args.sat_batch, hbm_peak, peak_src)
         if world == 1:
             step = cpu_forward_factory(sd, xs_h, Ss_h)
             threads, cap = pick_cpu_threads(step, budget_s=min(6.0, max(0.5, args.cpu_seconds)))
