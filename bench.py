@@ -368,23 +368,42 @@ def main():
         hx = [t.pin_memory() for t in xs_h]
         hS = [t.pin_memory() for t in Ss_h]
         hout = torch.empty(N_AGENTS, BATCH, 5).pin_memory()
-        e2e_steps = max(1, args.steps // 4)
+        e2e_steps = max(2, args.steps // 4)
         for i in range(max(3, args.warmup // 4)):
             model.infer_host(hx[i % unique], hS[i % unique], hout)
         barrier()
+        # (a) synchronous: one blocking host call per step
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            model.infer_host(hx[i % unique], hS[i % unique], hout)
+        torch.cuda.synchronize()
+        e2e_sync_s = time.perf_counter() - t0
+        barrier()
+        # (b) pipelined over independent episode batches (depth 2): step i is enqueued before step i-1
+        # is waited for, as a rollout driver advancing two batches of episodes alternately would do;
+        # every step still reads its x / S from pinned host memory and writes its logits back to it
+        houts = [torch.empty(N_AGENTS, BATCH, 5).pin_memory() for _ in range(2)]
+        checksum = 0.0
         with sampler:
             t0 = time.perf_counter()
+            prev = None
             for i in range(e2e_steps):
-                model.infer_host(hx[i % unique], hS[i % unique], hout)
+                tk = model.infer_host_async(hx[i % unique], hS[i % unique], houts[i & 1])
+                if prev is not None:
+                    model.wait(prev)
+                    checksum += float(houts[(i - 1) & 1][0, 0, 0])      # the step's result is read on the host
+                prev = tk
+            model.wait(prev)
+            checksum += float(houts[(e2e_steps - 1) & 1][0, 0, 0])
             torch.cuda.synchronize()
             e2e_s = time.perf_counter() - t0
         barrier()
 
     # ---- max over ranks --------------------------------------------------------------------
     if dist is not None:
-        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, e2e_sync_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms, e2e_s, e2e_sync_s = float(t[0]), float(t[1]), float(t[2])
     agent_steps = BATCH * N_AGENTS
     value = world * agent_steps * args.steps / (ms * 1e-3)
     e2e_value = world * agent_steps * e2e_steps / e2e_s
@@ -406,7 +425,10 @@ def main():
                                     % (pool_n * bytes_per_batch / 1e6, pool_n)},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
                     "h2d_bytes_per_step": bytes_per_batch, "d2h_bytes_per_step": N_AGENTS * BATCH * 5 * 4,
-                    "api": "DecentralPlannerNet.infer_host -> gpp_planner_forward_host (pinned host buffers)"},
+                    "api": "DecentralPlannerNet.infer_host_async/wait -> gpp_planner_forward_host_async (pinned host "
+                           "buffers, zero-copy), 2 independent episode batches in flight",
+                    "sync_value": world * agent_steps * e2e_steps / e2e_sync_s,
+                    "sync_api": "DecentralPlannerNet.infer_host -> gpp_planner_forward_host, one blocking call per step"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"kernel": "feature_kernel (CNN + compress MLP, fp32 FMA)", "bound": "tensor",

@@ -88,6 +88,9 @@ struct gpp_planner {
     size_t d_S_bytes;
     float* d_logits;
     size_t d_logits_floats;
+    // asynchronous host-buffer calls: completion tickets
+    cudaEvent_t tickets[16];
+    unsigned long long next_ticket;
     // per-kernel event log (roofline report)
     bool profiling;
     std::vector<cudaEvent_t>* events;   // triples: start, after feature kernel, after filter kernel
@@ -157,6 +160,8 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->d_S);
     cudaFree(p->d_logits);
     if (p->stream) cudaStreamDestroy(p->stream);
+    for (int i = 0; i < 16; ++i)
+        if (p->tickets[i]) cudaEventDestroy(p->tickets[i]);
     if (p->events) {
         for (cudaEvent_t e : *p->events) cudaEventDestroy(e);
         delete p->events;
@@ -349,6 +354,39 @@ static void* mapped_alias(const void* host_ptr) {
     }
     if (at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
     return nullptr;
+}
+
+extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const void* S_host,
+                                              int s_is_f64, float* logits_host, int B, int N,
+                                              unsigned long long* ticket) {
+    GPP_REQUIRE(p && x_host && S_host && logits_host && ticket, GPP_ERR_INVALID, "planner_forward_host_async: null pointer");
+    GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward_host_async: gpp_planner_set_weights not called");
+    GPP_REQUIRE(B >= 1 && N >= 1 && N <= 64, GPP_ERR_INVALID, "planner_forward_host_async: bad sizes B=%d N=%d", B, N);
+    void* mx = mapped_alias(x_host);
+    void* mS = mapped_alias(S_host);
+    void* ml = mapped_alias(logits_host);
+    GPP_REQUIRE(mx && mS && ml, GPP_ERR_INVALID,
+                "planner_forward_host_async: buffers must be pinned (page-locked) host memory");
+    const unsigned long long t = p->next_ticket;
+    cudaEvent_t& ev = p->tickets[t % 16];
+    if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    // the workspace between the two kernels is shared by the calls in flight; they are ordered on
+    // the planner's stream, so a later call's feature kernel starts after the earlier filter kernel
+    int rc = planner_forward_impl(p, reinterpret_cast<const float*>(mx), mS, s_is_f64,
+                                  reinterpret_cast<float*>(ml), nullptr, B, N, 0, p->stream);
+    if (rc) return rc;
+    GPP_CUDA_OK(cudaEventRecord(ev, p->stream));
+    p->next_ticket = t + 1;
+    *ticket = t;
+    return GPP_OK;
+}
+
+extern "C" int gpp_planner_wait(gpp_planner* p, unsigned long long ticket) {
+    GPP_REQUIRE(p, GPP_ERR_INVALID, "planner_wait: null planner");
+    GPP_REQUIRE(ticket < p->next_ticket && ticket + 16 >= p->next_ticket, GPP_ERR_INVALID,
+                "planner_wait: ticket %llu is not among the 16 most recent calls", ticket);
+    GPP_CUDA_OK(cudaEventSynchronize(p->tickets[ticket % 16]));
+    return GPP_OK;
 }
 
 extern "C" int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,

@@ -241,6 +241,34 @@ class DecentralPlannerNet(nn.Module):
                 out_host.data_ptr(), B, N))
         return out_host
 
+    def infer_host_async(self, x_host: torch.Tensor, S_host: torch.Tensor, out_host: torch.Tensor, device=None) -> int:
+        """Pipelined variant of `infer_host` for rollouts over several independent episode batches:
+        enqueues the zero-copy forward and returns a ticket at once; `wait(ticket)` blocks until that
+        step's logits are in `out_host`.  All three tensors must be pinned and must not be touched in
+        between.  Steps execute in issue order."""
+        assert not self.training, "infer_host_async is the eval-mode rollout path"
+        assert x_host.is_pinned() and S_host.is_pinned() and out_host.is_pinned(), "pinned host tensors required"
+        assert x_host.dtype == torch.float32 and x_host.is_contiguous() and S_host.is_contiguous()
+        assert S_host.dim() == 3 and S_host.dtype in (torch.float32, torch.float64)
+        B, N = x_host.shape[0], x_host.shape[1]
+        assert tuple(out_host.shape) == (N, B, 5) and out_host.dtype == torch.float32 and out_host.is_contiguous()
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        nat = self._native_for(dev)
+        if getattr(nat, "fresh", False):
+            torch.cuda.current_stream(dev).synchronize()
+            nat.fresh = False
+        t = C.c_ulonglong()
+        with torch.cuda.device(dev):
+            _lib.check(nat.lib.gpp_planner_forward_host_async(
+                nat.handle, x_host.data_ptr(), S_host.data_ptr(), int(S_host.dtype == torch.float64),
+                out_host.data_ptr(), B, N, C.byref(t)))
+        self.__dict__["_async_native"] = nat
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        nat = self.__dict__["_async_native"]
+        _lib.check(nat.lib.gpp_planner_wait(nat.handle, C.c_ulonglong(ticket)))
+
     # ------------------------------------------------ autograd (training) path
     def _bn_per_agent(self, h, bn, N):
         """BatchNorm2d with the reference's per-agent semantics: the reference calls

@@ -144,6 +144,15 @@ int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_
 int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,
                              int s_is_f64, float* logits_host, int B, int N);
 
+/* Asynchronous variant for pipelined rollouts over independent episode batches: enqueues the same
+ * zero-copy forward on the planner's stream and returns at once with a completion ticket; the host
+ * buffers MUST be pinned and must stay untouched until gpp_planner_wait(ticket) returns.  Calls are
+ * executed in issue order; at most 16 tickets may be outstanding. */
+int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const void* S_host,
+                                   int s_is_f64, float* logits_host, int B, int N,
+                                   unsigned long long* ticket);
+int gpp_planner_wait(gpp_planner* p, unsigned long long ticket);
+
 /* Which graph-filter kernel the planner uses: 0 = automatic (tensor cores once B*N >= 4096 node
  * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 3xTF32 kernel (gf_fwd_tc_kernel;
  * GPP_ERR_UNSUPPORTED at forward time if N/K do not fit its 128-row tile). */
@@ -152,6 +161,10 @@ int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode);
 /* Test hook for the tcgen05 plumbing: D[128][128] = A[128][32] . B[128][32]^T on the tensor cores
  * (A, B tf32-representable fp32, row-major, device memory). */
 int gpp_debug_umma_selftest(const float* A, const float* B, float* D, void* stream);
+
+/* Debug: per-phase cycle totals of the tcgen05 filter kernel (filled only when the environment variable
+ * GPP_TC_TIMING is set): staging loop, wait for the last MMA, TMEM read-out, propagation, stores, tiles. */
+int gpp_debug_tc_timing(unsigned long long* out6);
 
 /* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
  * CUDA events before / between / after its two kernels on the launching stream (at most 8192

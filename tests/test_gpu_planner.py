@@ -122,3 +122,19 @@ def test_api_asserts():
     m.addGSO(torch.rand(2, 4, 4).cuda())
     with pytest.raises(RuntimeError):
         m(torch.rand(2, 4, 3, 11, 11))                # CPU tensor: no fallback
+
+
+def test_async_host_calls_match_sync(golden):
+    g = golden("planner_K3.npz")
+    N, K, B = int(g["N"]), int(g["K"]), int(g["B"])
+    m = _model(_sd(g), N, K).eval()
+    x = torch.from_numpy(g["x"].astype(np.float32)).pin_memory()
+    S = torch.from_numpy(g["S"]).pin_memory()
+    outs = [torch.empty(N, B, 5).pin_memory() for _ in range(3)]
+    tickets = [m.infer_host_async(x, S, o) for o in outs]
+    for t in reversed(tickets):
+        m.wait(t)
+    for o in outs:
+        assert rel_err(o.numpy(), g["eval_logits"]) <= TOL
+    with pytest.raises(AssertionError):
+        m.infer_host_async(torch.from_numpy(g["x"].astype(np.float32)), S, outs[0])     # pageable memory
