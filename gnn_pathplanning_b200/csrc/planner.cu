@@ -88,9 +88,15 @@ struct gpp_planner {
     size_t d_S_bytes;
     float* d_logits;
     size_t d_logits_floats;
-    // asynchronous host-buffer calls: completion tickets
+    // asynchronous host-buffer calls: completion tickets + double-buffered H2D staging on a copy stream
     cudaEvent_t tickets[16];
     unsigned long long next_ticket;
+    cudaStream_t copy_stream;
+    float* a_x[2];
+    size_t a_x_floats[2];
+    void* a_S[2];
+    size_t a_S_bytes[2];
+    cudaEvent_t copied[2];
     // per-kernel event log (roofline report)
     bool profiling;
     std::vector<cudaEvent_t>* events;   // triples: start, after feature kernel, after filter kernel
@@ -162,6 +168,12 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int i = 0; i < 16; ++i)
         if (p->tickets[i]) cudaEventDestroy(p->tickets[i]);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->a_x[i]);
+        cudaFree(p->a_S[i]);
+        if (p->copied[i]) cudaEventDestroy(p->copied[i]);
+    }
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     if (p->events) {
         for (cudaEvent_t e : *p->events) cudaEventDestroy(e);
         delete p->events;
@@ -367,13 +379,42 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     void* ml = mapped_alias(logits_host);
     GPP_REQUIRE(mx && mS && ml, GPP_ERR_INVALID,
                 "planner_forward_host_async: buffers must be pinned (page-locked) host memory");
+    (void)mx; (void)mS;
     const unsigned long long t = p->next_ticket;
     cudaEvent_t& ev = p->tickets[t % 16];
     if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    // the workspace between the two kernels is shared by the calls in flight; they are ordered on
-    // the planner's stream, so a later call's feature kernel starts after the earlier filter kernel
-    int rc = planner_forward_impl(p, reinterpret_cast<const float*>(mx), mS, s_is_f64,
-                                  reinterpret_cast<float*>(ml), nullptr, B, N, 0, p->stream);
+    // Pipelined path: the inputs of this step travel by DMA on a copy stream into one of two device
+    // slots while the kernels of the previous step run on the compute stream (a kernel that reads its
+    // input straight over PCIe cannot overlap that read with its own compute); the logits are still
+    // written straight into the pinned host buffer.  Slot reuse waits for the step two tickets back.
+    const int slot = (int)(t & 1);
+    const size_t nx = (size_t)B * N * IN_PIX;
+    const size_t sb = (size_t)B * N * N * (s_is_f64 ? 8 : 4);
+    if (!p->copy_stream) GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+    if (!p->copied[slot]) GPP_CUDA_OK(cudaEventCreateWithFlags(&p->copied[slot], cudaEventDisableTiming));
+    if (p->a_x_floats[slot] < nx || p->a_S_bytes[slot] < sb) {
+        GPP_CUDA_OK(cudaStreamSynchronize(p->stream));
+        GPP_CUDA_OK(cudaStreamSynchronize(p->copy_stream));
+        if (p->a_x_floats[slot] < nx) {
+            cudaFree(p->a_x[slot]); p->a_x[slot] = nullptr; p->a_x_floats[slot] = 0;
+            GPP_CUDA_OK(cudaMalloc(&p->a_x[slot], sizeof(float) * nx));
+            p->a_x_floats[slot] = nx;
+        }
+        if (p->a_S_bytes[slot] < sb) {
+            cudaFree(p->a_S[slot]); p->a_S[slot] = nullptr; p->a_S_bytes[slot] = 0;
+            GPP_CUDA_OK(cudaMalloc(&p->a_S[slot], sb));
+            p->a_S_bytes[slot] = sb;
+        }
+    }
+    if (t >= 2) GPP_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->tickets[(t - 2) % 16], 0));
+    GPP_CUDA_OK(cudaMemcpyAsync(p->a_x[slot], x_host, sizeof(float) * nx, cudaMemcpyHostToDevice, p->copy_stream));
+    GPP_CUDA_OK(cudaMemcpyAsync(p->a_S[slot], S_host, sb, cudaMemcpyHostToDevice, p->copy_stream));
+    GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));
+    GPP_CUDA_OK(cudaStreamWaitEvent(p->stream, p->copied[slot], 0));
+    // the feature workspace between the two kernels is shared by the calls in flight; they are ordered
+    // on the compute stream, so a later call's feature kernel starts after the earlier filter kernel
+    int rc = planner_forward_impl(p, p->a_x[slot], p->a_S[slot], s_is_f64, reinterpret_cast<float*>(ml),
+                                  nullptr, B, N, 1, p->stream);
     if (rc) return rc;
     GPP_CUDA_OK(cudaEventRecord(ev, p->stream));
     p->next_ticket = t + 1;
