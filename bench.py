@@ -426,8 +426,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
                     "h2d_bytes_per_step": bytes_per_batch, "d2h_bytes_per_step": N_AGENTS * BATCH * 5 * 4,
                     "api": "DecentralPlannerNet.infer_host_async/wait -> gpp_planner_forward_host_async (pinned host "
-                           "buffers; H2D by DMA on a copy stream overlapping the previous step's kernels, logits "
-                           "written straight to host), 2 independent episode batches in flight",
+                           "buffers; inputs staged by a small copy kernel on a second stream while the previous step's "
+                           "kernels run, logits written straight to host), 2 independent episode batches in flight",
                     "sync_value": world * agent_steps * e2e_steps / e2e_sync_s,
                     "sync_api": "DecentralPlannerNet.infer_host -> gpp_planner_forward_host, one blocking call per step"},
             "gpu_launches": int(launches),

@@ -51,6 +51,17 @@ int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const floa
                          float* y, const float* wa, const float* ba, float* logits, int B, int N, int K,
                          int relu, int allow_bulk, cudaStream_t st);
 
+// Host -> device staging as a kernel: a few CTAs pull pinned (device-mapped) host memory over PCIe with
+// 16-byte loads and store it to HBM.  Runs on the copy stream next to the compute kernels of the previous
+// step (they leave SMs free at rollout batch sizes); n16 = number of 16-byte units, tail bytes separately.
+__global__ void __launch_bounds__(256) stage_h2d_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                        size_t n16, const unsigned char* src_tail,
+                                                        unsigned char* dst_tail, int tail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
 // scale = gamma / sqrt(var + eps);  shift = (conv_bias - mean) * scale + beta
 __global__ void fold_bn_kernel(const float* conv_b, const float* g, const float* b, const float* mean,
                                const float* var, float* sc, float* sh, int C) {
@@ -379,12 +390,13 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     void* ml = mapped_alias(logits_host);
     GPP_REQUIRE(mx && mS && ml, GPP_ERR_INVALID,
                 "planner_forward_host_async: buffers must be pinned (page-locked) host memory");
-    (void)mx; (void)mS;
+    GPP_REQUIRE((reinterpret_cast<uintptr_t>(mx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(mS) & 15u) == 0,
+                GPP_ERR_INVALID, "planner_forward_host_async: host buffers must be 16-byte aligned");
     const unsigned long long t = p->next_ticket;
     cudaEvent_t& ev = p->tickets[t % 16];
     if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    // Pipelined path: the inputs of this step travel by DMA on a copy stream into one of two device
-    // slots while the kernels of the previous step run on the compute stream (a kernel that reads its
+    // Pipelined path: the inputs of this step are pulled over PCIe by a small staging kernel on a copy
+    // stream into one of two device slots while the kernels of the previous step run on the compute stream (a kernel that reads its
     // input straight over PCIe cannot overlap that read with its own compute); the logits are still
     // written straight into the pinned host buffer.  Slot reuse waits for the step two tickets back.
     const int slot = (int)(t & 1);
@@ -407,8 +419,19 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
         }
     }
     if (t >= 2) GPP_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->tickets[(t - 2) % 16], 0));
-    GPP_CUDA_OK(cudaMemcpyAsync(p->a_x[slot], x_host, sizeof(float) * nx, cudaMemcpyHostToDevice, p->copy_stream));
-    GPP_CUDA_OK(cudaMemcpyAsync(p->a_S[slot], S_host, sb, cudaMemcpyHostToDevice, p->copy_stream));
+    {
+        const size_t xb = sizeof(float) * nx;
+        stage_h2d_kernel<<<8, 256, 0, p->copy_stream>>>(
+            reinterpret_cast<const uint4*>(mx), reinterpret_cast<uint4*>(p->a_x[slot]), xb / 16,
+            reinterpret_cast<const unsigned char*>(mx) + (xb / 16) * 16,
+            reinterpret_cast<unsigned char*>(p->a_x[slot]) + (xb / 16) * 16, (int)(xb % 16));
+        GPP_LAUNCH_CHECK();
+        stage_h2d_kernel<<<1, 256, 0, p->copy_stream>>>(
+            reinterpret_cast<const uint4*>(mS), reinterpret_cast<uint4*>(p->a_S[slot]), sb / 16,
+            reinterpret_cast<const unsigned char*>(mS) + (sb / 16) * 16,
+            reinterpret_cast<unsigned char*>(p->a_S[slot]) + (sb / 16) * 16, (int)(sb % 16));
+        GPP_LAUNCH_CHECK();
+    }
     GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));
     GPP_CUDA_OK(cudaStreamWaitEvent(p->stream, p->copied[slot], 0));
     // the feature workspace between the two kernels is shared by the calls in flight; they are ordered
