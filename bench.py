@@ -202,7 +202,11 @@ def saturated_filter_roofline(gp, dev, batch, hbm_peak, peak_src):
     w = ((torch.rand(128, 1, K_TAPS, 128, generator=g) - 0.5) * 0.2).to(dev)
     b = (torch.rand(128, 1, generator=g) - 0.5).to(dev)
     x = torch.randn(batch, N_AGENTS, 128, device=dev)
-    S = torch.rand(batch, N_AGENTS, N_AGENTS, device=dev) * 0.2
+    # rollout-like GSOs: normalised adjacency of random agent positions on the 20x20 map, radius 6
+    pos = torch.randint(0, MAP_W, (batch, N_AGENTS, 2), device=dev).float()
+    A = ((pos[:, :, None, :] - pos[:, None, :, :]).norm(dim=-1) < 6.0).float() * (1.0 - torch.eye(N_AGENTS, device=dev))
+    dinv = A.sum(-1).clamp(min=1.0).rsqrt() * (A.sum(-1) > 0)
+    S = (dinv[:, :, None] * A * dinv[:, None, :]).contiguous()
     for _ in range(3):
         gp.graph_filter(x, S, w, b, True, gp.NODE_MAJOR, gp.NODE_MAJOR)
     torch.cuda.synchronize()

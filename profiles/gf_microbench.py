@@ -20,7 +20,11 @@ b = (torch.rand(128, 1) - 0.5).cuda()
 out = []
 for B in (64, 512, 4096, 32768, 131072):
     x = torch.randn(B, N, 128, device="cuda")
-    S = (torch.rand(B, N, N, device="cuda") * 0.2)
+    # rollout-like GSO: normalised adjacency of random agent positions on a 20x20 map, radius 6
+    pos = torch.randint(0, 20, (B, N, 2), device="cuda").float()
+    A = ((pos[:, :, None, :] - pos[:, None, :, :]).norm(dim=-1) < 6.0).float() * (1.0 - torch.eye(N, device="cuda"))
+    dinv = A.sum(-1).clamp(min=1.0).rsqrt() * (A.sum(-1) > 0)
+    S = (dinv[:, :, None] * A * dinv[:, None, :]).contiguous()
     iters = max(5, min(200, int(2e6 / (B * N))))
     for _ in range(3):
         y = gp.graph_filter(x, S, w, b, True, gp.NODE_MAJOR, gp.NODE_MAJOR)
