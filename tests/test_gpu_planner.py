@@ -138,3 +138,74 @@ def test_async_host_calls_match_sync(golden):
         assert rel_err(o.numpy(), g["eval_logits"]) <= TOL
     with pytest.raises(AssertionError):
         m.infer_host_async(torch.from_numpy(g["x"].astype(np.float32)), S, outs[0])     # pageable memory
+
+
+@pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (20, 3, 16, 28)])
+def test_train_step_vs_oracle_at_config_sizes(N, K, B, map_w):
+    """BASELINE configs 3 / 5 (per-GPU shard): one training forward/backward against the CPU oracle's
+    autograd -- logits, loss, every gradient, BatchNorm running statistics."""
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    sd = po.init_state_dict(K, seed=11)
+    po.randomize_bn_stats(sd, seed=3)
+    x, S = synthetic.make_batch(B, N, map_w, seed=21)
+    tgt = torch.from_numpy(synthetic.random_targets(B, N, seed=5))
+    xt, St = torch.from_numpy(x), torch.from_numpy(S)
+    bn = {k: v.clone() for k, v in sd.items() if "running" in k or "tracked" in k}
+    leaf = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v)
+            for k, v in sd.items()}
+    ref_out = po.planner_forward(leaf, St, xt, True, bn)
+    ref_loss = po.planner_loss(ref_out, tgt)
+    ref_loss.backward()
+    m = _model(sd, N, K).train()
+    m.addGSO(St.cuda())
+    out = m(xt.cuda())
+    loss = po.planner_loss(out, tgt.cuda())
+    loss.backward()
+    assert rel_err(torch.stack(out).detach().cpu().numpy(), torch.stack(ref_out).detach().numpy()) <= TOL
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * max(1.0, abs(ref_loss.item()))
+    for n_, p in m.named_parameters():
+        ref = leaf[n_].grad.numpy()
+        if n_.startswith("ConvLayers") and n_.endswith("bias") and int(n_.split(".")[1]) in (0, 4, 7, 11, 14):
+            assert np.abs(p.grad.cpu().numpy() - ref).max() <= 1e-5      # true gradient is 0 (BatchNorm follows)
+        else:
+            assert rel_err(p.grad.cpu().numpy(), ref) <= 5e-5, n_
+    after = m.state_dict()
+    for k, v in bn.items():
+        assert rel_err(after[k].double().cpu().numpy(), v.double().numpy()) <= TOL, k
+
+
+def test_optimizer_steps_follow_oracle():
+    """Three Adam steps (lr 1e-3, wd 1e-5: agents/decentralplannerlocal.py:59) on the CUDA module and on
+    the CPU oracle stay together -- the weight-arena refresh after in-place updates is exercised too."""
+    from gnn_pathplanning_b200 import synthetic, sharding
+    from oracle import planner_oracle as po
+    N, K, B = 6, 2, 12
+    sd = po.init_state_dict(K, seed=2)
+    x, S = synthetic.make_batch(B, N, 12, seed=4)
+    tgt = torch.from_numpy(synthetic.random_targets(B, N, seed=6))
+    xt, St = torch.from_numpy(x), torch.from_numpy(S)
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    leaf = {k: sd[k].clone().requires_grad_(True) for k in names}
+    full = dict(sd)
+    bn = {k: v.clone() for k, v in sd.items() if "running" in k or "tracked" in k}
+    opt_ref = torch.optim.Adam([leaf[k] for k in names], lr=1e-3, weight_decay=1e-5)
+    m = _model(sd, N, K).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    bucket = sharding.GradientBucket(m)
+    for _ in range(3):
+        opt_ref.zero_grad()
+        full.update(leaf)
+        l_ref = po.planner_loss(po.planner_forward(full, St, xt, True, bn), tgt)
+        l_ref.backward()
+        opt_ref.step()
+        l = sharding.train_step(m, opt, bucket, xt.cuda(), St.cuda(), tgt.cuda(), B)
+        assert abs(l.item() - l_ref.item()) <= 2e-5 * max(1.0, abs(l_ref.item()))
+    m.eval()
+    with torch.no_grad():
+        m.addGSO(St.cuda())
+        got = torch.stack(m(xt.cuda())).cpu().numpy()
+        full.update({k: v.detach() for k, v in leaf.items()})
+        full.update(bn)
+        ref = torch.stack(po.planner_forward(full, St, xt)).numpy()
+    assert rel_err(got, ref) <= 1e-4       # three optimiser steps amplify fp32 rounding differences
