@@ -280,6 +280,8 @@ def main():
     ap.add_argument("--pool-mb", type=float, default=160.0, help="device input pool size (> L2)")
     ap.add_argument("--gf-mode", default="auto", choices=["auto", "cuda", "tc"],
                     help="graph-filter kernel of the planner: auto / CUDA-core / tcgen05")
+    ap.add_argument("--fe-mode", default="auto", choices=["auto", "cuda", "tc"],
+                    help="feature-extractor (CNN) kernel of the planner: auto / CUDA-core / tcgen05")
     ap.add_argument("--sat-batch", type=int, default=32768,
                     help="episodes in the saturated graph-filter roofline measurement (0 = skip)")
     args = ap.parse_args()
@@ -314,6 +316,7 @@ def main():
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     model.set_graph_filter_mode(args.gf_mode)
+    model.set_feature_mode(args.fe_mode)
 
     # ---- inputs: a few unique synthetic batches, replicated (sample-permuted) into a pool > L2
     unique = 8

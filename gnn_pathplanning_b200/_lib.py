@@ -14,7 +14,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgnnpp_b200.so")
-SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "feature.cu", "planner.cu")
+SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "feature.cu", "feature_tc.cu", "planner.cu")
 HEADERS = ("common.cuh", "feature.cuh", "tc_common.cuh")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200.h")
 
@@ -38,7 +38,7 @@ EXPORTED = (
     "gpp_planner_forward", "gpp_planner_forward_host",
     "gpp_planner_forward_host_async", "gpp_planner_wait", "gpp_debug_tc_timing",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
-    "gpp_planner_set_graph_filter_mode", "gpp_debug_umma_selftest",
+    "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode", "gpp_debug_umma_selftest",
     "gpp_launch_count", "gpp_reset_launch_count",
 )
 
@@ -130,6 +130,8 @@ def load():
         lib.gpp_planner_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i)]
         lib.gpp_planner_set_graph_filter_mode.restype = i
         lib.gpp_planner_set_graph_filter_mode.argtypes = [vp, i]
+        lib.gpp_planner_set_feature_mode.restype = i
+        lib.gpp_planner_set_feature_mode.argtypes = [vp, i]
         lib.gpp_debug_umma_selftest.restype = i
         lib.gpp_debug_umma_selftest.argtypes = [vp, vp, vp, vp]
         lib.gpp_launch_count.restype = C.c_ulonglong

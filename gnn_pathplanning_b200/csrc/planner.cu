@@ -62,6 +62,11 @@ __global__ void __launch_bounds__(256) stage_h2d_kernel(const uint4* __restrict_
     if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
 
+// tensor-core feature extractor (feature_tc.cu)
+size_t feature_tc_image_floats(int L);
+int launch_prep_feature_tc(const float* w, float* img, int L, cudaStream_t st);
+int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStream_t st);
+
 // scale = gamma / sqrt(var + eps);  shift = (conv_bias - mean) * scale + beta
 __global__ void fold_bn_kernel(const float* conv_b, const float* g, const float* b, const float* mean,
                                const float* var, float* sc, float* sh, int C) {
@@ -86,6 +91,8 @@ struct gpp_planner {
     size_t off_sc[5], off_sh[5];
     size_t off_b5, off_gfw, off_gfb, off_wa, off_ba, off_gfimg, arena_floats;
     int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
+    int fe_mode;         // feature extractor: 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
+    size_t off_fimg[6];  // tcgen05 filter chunk images of conv0..4 and the compress MLP
     bool weights_set;
     float* raw;          // device staging for host-provided parameters
     size_t raw_floats;
@@ -152,6 +159,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     p->off_wa = take(5 * 128);
     p->off_ba = take(64);
     p->off_gfimg = take(gf_tc_image_floats(K));      // pre-split, pre-swizzled tcgen05 B-operand chunks
+    for (int l = 0; l < 6; ++l) p->off_fimg[l] = take(feature_tc_image_floats(l));
     p->arena_floats = off;
     if (cudaMalloc(&p->arena, sizeof(float) * off) != cudaSuccess) {
         set_error("planner_create: cudaMalloc(%zu) failed", sizeof(float) * off);
@@ -195,6 +203,12 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
 extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
     GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_graph_filter_mode: mode must be 0, 1 or 2");
     p->gf_mode = mode;
+    return GPP_OK;
+}
+
+extern "C" int gpp_planner_set_feature_mode(gpp_planner* p, int mode) {
+    GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_feature_mode: mode must be 0, 1 or 2");
+    p->fe_mode = mode;
     return GPP_OK;
 }
 
@@ -284,6 +298,10 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
                                                          d.bn_var[l], A + p->off_sc[l], A + p->off_sh[l], C);
         GPP_LAUNCH_CHECK();
     }
+    for (int l = 0; l < 6; ++l) {
+        int rcf = launch_prep_feature_tc(l < 5 ? d.conv_w[l] : d.compress_w, A + p->off_fimg[l], l, st);
+        if (rcf) return rcf;
+    }
     int rc = launch_transpose_taps(d.compress_w, A + p->off_w[5], 128, 128, st);
     if (rc) return rc;
     rc = launch_transpose_taps(d.gf_w, A + p->off_gfw, 128, K * 128, st);
@@ -337,7 +355,14 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         GPP_REQUIRE(e0 && e1 && e2, GPP_ERR_CUDA, "planner_forward: cudaEventCreate failed");
         GPP_CUDA_OK(cudaEventRecord(e0, st));
     }
-    int rc = launch_feature_kernel(fa, st);
+    int rc;
+    if (p->fe_mode == 2 || (p->fe_mode == 0 && rows >= 256)) {
+        const float* imgs[6];
+        for (int l = 0; l < 6; ++l) imgs[l] = A + p->off_fimg[l];
+        rc = launch_feature_tc_kernel(fa, imgs, st);
+    } else {
+        rc = launch_feature_kernel(fa, st);
+    }
     if (rc) return rc;
     if (prof) GPP_CUDA_OK(cudaEventRecord(e1, st));
     const bool tc_fits = gf_tc_tile_samples(N, p->K) > 0;

@@ -81,6 +81,7 @@ class _NativePlanner:
         self.handle = h
         self.key = None
         self.gf_mode = None
+        self.fe_mode = None
 
     def __del__(self):
         try:
@@ -195,11 +196,19 @@ class DecentralPlannerNet(nn.Module):
         if nat.gf_mode != mode:
             _lib.check(nat.lib.gpp_planner_set_graph_filter_mode(nat.handle, mode))
             nat.gf_mode = mode
+        fmode = self.__dict__.get("_fe_mode", 0)
+        if nat.fe_mode != fmode:
+            _lib.check(nat.lib.gpp_planner_set_feature_mode(nat.handle, fmode))
+            nat.fe_mode = fmode
         return nat
 
     def set_graph_filter_mode(self, mode: str) -> None:
         """'auto' (default), 'cuda' (fp32 CUDA-core kernel) or 'tc' (tcgen05 3xTF32 kernel)."""
         self.__dict__["_gf_mode"] = {"auto": 0, "cuda": 1, "tc": 2}[mode]
+
+    def set_feature_mode(self, mode: str) -> None:
+        """Feature extractor kernel: 'auto' (default), 'cuda' (fp32 CUDA cores) or 'tc' (tcgen05 3xTF32)."""
+        self.__dict__["_fe_mode"] = {"auto": 0, "cuda": 1, "tc": 2}[mode]
 
     def _forward_fused(self, x, S):
         B, N = x.shape[0], x.shape[1]

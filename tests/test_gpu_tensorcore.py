@@ -33,13 +33,36 @@ def test_umma_selftest_exact():
     assert np.array_equal(D.cpu().numpy().astype(np.float64), ref)
 
 
-def _model(sd, N, K, mode):
+def _model(sd, N, K, mode, fe_mode="cuda"):
     import gnn_pathplanning_b200 as gp
     m = gp.DecentralPlannerNet(Cfg(N, K))
     m.load_state_dict(sd)
     m = m.cuda().eval()
     m.set_graph_filter_mode(mode)
+    m.set_feature_mode(fe_mode)
     return m
+
+
+@pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (10, 3, 1, 20), (7, 2, 3, 12), (20, 3, 40, 28), (40, 3, 7, 50),
+                                         (1, 3, 9, 8), (10, 3, 500, 20), (3, 1, 101, 12)])
+def test_planner_tc_feature_extractor_vs_oracle(N, K, B, map_w):
+    """tcgen05 implicit-GEMM CNN + compress MLP (feature_tc_kernel) against the CPU oracle."""
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    sd = po.init_state_dict(K, seed=N + K + 1)
+    po.randomize_bn_stats(sd, seed=B + 1)
+    x, S = synthetic.make_batch(B, N, map_w, seed=B + N + 1)
+    xt, St = torch.from_numpy(x), torch.from_numpy(S)
+    with torch.no_grad():
+        ref = torch.stack(po.planner_forward(sd, St, xt)).numpy()
+        m = _model(sd, N, K, "cuda", "tc")
+        m.addGSO(St.cuda())
+        got = torch.stack(m(xt.cuda())).cpu().numpy()
+    print("tc feature extractor rel err %.3e" % rel_err(got, ref))
+    assert rel_err(got, ref) <= TOL
+    top2 = np.sort(ref, -1)
+    clear = (top2[..., -1] - top2[..., -2]) > 1e-4 * np.abs(ref).max()
+    assert np.array_equal(got.argmax(-1)[clear], ref.argmax(-1)[clear])
 
 
 @pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (10, 3, 13, 20), (20, 3, 40, 28), (40, 3, 7, 50),
