@@ -21,6 +21,8 @@
 #include "feature.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace gpp {
 
 constexpr int FT_THREADS = 256;            // producer / epilogue threads (+ 32 for the MMA warp)
@@ -50,6 +52,7 @@ struct FtArgs {
     float* feat;
     int total_agents, apt, num_tiles;
     FtLayer layer[FT_NLAYERS];
+    unsigned long long* timing;    // optional [20] cycle counters (debug): per layer produce / wait / epilogue
 };
 
 // compile-time layer table
@@ -63,8 +66,16 @@ __host__ __device__ constexpr int ft_cin(int L) { return L == 0 ? 3 : L < 3 ? 32
 // floats per agent of the NHWC output of layer L (after pooling)
 __host__ __device__ constexpr int ft_out_stride(int L) { return L < 2 ? 800 : L < 4 ? 256 : 128; }
 
+// One arrival per producer WARP (barrier count = 8) and one polling lane per warp: 256 threads arriving on /
+// polling the same mbarrier serialise in the shared-memory atomic unit and cost ~1000 cycles per item.
 __device__ __forceinline__ void ft_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 __device__ __forceinline__ void ft_producers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -97,7 +108,7 @@ __device__ __forceinline__ void ft_produce_layer(const FtArgs& A, unsigned char*
         {   // B chunk kc -> B stage
             const int bs = gb % FT_NB_STAGES;
             const uint32_t use = gb / FT_NB_STAGES;
-            if (use >= 1) mbar_wait(&doneB[bs], (use - 1) & 1);
+            if (use >= 1) ft_mbar_wait_warp(&doneB[bs], (use - 1) & 1);
             const uint32_t dst = smem_u32(sm + FT_OFF_B + bs * FT_STAGE_BYTES);
             const char* src = img + (size_t)kc * B_BYTES;
             for (int u = tid; u < B_BYTES / 16; u += FT_THREADS)
@@ -113,7 +124,7 @@ __device__ __forceinline__ void ft_produce_layer(const FtArgs& A, unsigned char*
         for (int mt = 0; mt < ntiles; ++mt, ++ga) {
             const int as = ga % FT_NA_STAGES;
             const uint32_t ause = ga / FT_NA_STAGES;
-            if (ause >= 1) mbar_wait(&doneA[as], (ause - 1) & 1);
+            if (ause >= 1) ft_mbar_wait_warp(&doneA[as], (ause - 1) & 1);
             unsigned char* stage = sm + FT_OFF_A + as * FT_STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -208,14 +219,14 @@ __device__ __forceinline__ void ft_epilogue_layer(const FtArgs& A, float* out_bu
     constexpr int N = ft_n(L), ROWS = ft_rows(L);
     constexpr int NB = (N == 32) ? 1 : N / 64;          // 32-column batches per thread
     const int h = warp >> 2;
-    if (N == 32 && h == 1) return;                        // 32 columns: one thread per row is enough
+    // N = 32: one thread per row covers all columns, so the two warp groups take alternate M tiles instead
     const int col0 = (N == 32) ? 0 : h * (N / 2);
     const int ntiles = (na * ROWS + 127) >> 7;
     const int r = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);
     const float* sc = A.layer[L].sc;
     const float* sh = A.layer[L].sh;
-    for (int mt = 0; mt < ntiles; ++mt) {
+    for (int mt = (N == 32) ? h : 0; mt < ntiles; mt += (N == 32) ? 2 : 1) {
         const int m = mt * 128 + r;
         const int a = m / ROWS, idx = m - a * ROWS;
         const bool valid = a < na;
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
 
     if (tid == 0) {
         for (int i = 0; i < FT_NA_STAGES + FT_NB_STAGES; ++i) mbar_init(&bars[i], 1);
-        for (int i = 0; i < FT_NA_STAGES + FT_NB_STAGES; ++i) mbar_init(&fullA[i], FT_THREADS);
+        for (int i = 0; i < FT_NA_STAGES + FT_NB_STAGES; ++i) mbar_init(&fullA[i], FT_THREADS / 32);
         mbar_init(layer_done, 1);
         fence_mbar_init();
     }
@@ -293,6 +304,8 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
     } else {
         // ================= producers + epilogue =================
         uint32_t nlayer = 0;        // layer_done phases consumed
+        unsigned long long tacc[20];
+        for (int i = 0; i < 20; ++i) tacc[i] = 0;
         for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x) {
             const int a0 = tile * A.apt;
             const int na = min(A.apt, A.total_agents - a0);
@@ -309,13 +322,20 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
             ft_producers_sync();
 
 #define FT_LAYER(Lx, IN, OUT)                                                                                 \
-    ft_produce_layer<Lx>(A, sm, IN, na, doneA, doneB, fullA, fullB, ga, gb, tid);                              \
-    mbar_wait(layer_done, nlayer & 1);                                                                         \
-    ++nlayer;                                                                                                  \
-    tcgen05_fence_after();                                                                                     \
-    ft_epilogue_layer<Lx>(A, OUT, na, a0, tmem_acc, warp, lane);                                               \
-    tcgen05_fence_before();                                                                                    \
-    ft_producers_sync();
+    {                                                                                                          \
+        const long long t0 = clock64();                                                                        \
+        ft_produce_layer<Lx>(A, sm, IN, na, doneA, doneB, fullA, fullB, ga, gb, tid);                          \
+        const long long t1 = clock64();                                                                        \
+        ft_mbar_wait_warp(layer_done, nlayer & 1);                                                             \
+        ++nlayer;                                                                                              \
+        tcgen05_fence_after();                                                                                 \
+        const long long t2 = clock64();                                                                        \
+        ft_epilogue_layer<Lx>(A, OUT, na, a0, tmem_acc, warp, lane);                                           \
+        tcgen05_fence_before();                                                                                \
+        ft_producers_sync();                                                                                   \
+        const long long t3 = clock64();                                                                        \
+        tacc[3 * Lx] += t1 - t0; tacc[3 * Lx + 1] += t2 - t1; tacc[3 * Lx + 2] += t3 - t2;                     \
+    }
 
             FT_LAYER(0, regY, regX)      // in0  -> act1 [a][25][32]
             FT_LAYER(1, regX, regY)      // act1 -> act2 [a][25][32]
@@ -324,7 +344,10 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
             FT_LAYER(4, regY, regX)      // act4 -> act5 [a][128]
             FT_LAYER(5, regX, regY)      // act5 -> features (global)
 #undef FT_LAYER
+            tacc[18] += 1;
         }
+        if (A.timing && tid == 0)
+            for (int i = 0; i < 20; ++i) atomicAdd(&A.timing[i], tacc[i]);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -359,6 +382,15 @@ __global__ void prep_umma_conv_kernel(const float* __restrict__ w, float* __rest
     base[N * 32 + off] = lo;
 }
 
+static unsigned long long* g_ft_timing = nullptr;
+int debug_feature_tc_timing(unsigned long long* out20) {
+    if (!g_ft_timing) return GPP_ERR_INVALID;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out20, g_ft_timing, 160, cudaMemcpyDeviceToHost);
+    cudaMemset(g_ft_timing, 0, 160);
+    return GPP_OK;
+}
+
 size_t feature_tc_image_floats(int L) { return (size_t)ft_nk(L) * 2 * ft_n(L) * 32; }
 
 int launch_prep_feature_tc(const float* w, float* img, int L, cudaStream_t st) {
@@ -383,6 +415,11 @@ int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStr
     if (apt > FT_AMAX) apt = FT_AMAX;
     a.apt = apt;
     a.num_tiles = (fa.total_agents + apt - 1) / apt;
+    a.timing = nullptr;
+    if (getenv("GPP_TC_TIMING")) {
+        if (!g_ft_timing) { cudaMalloc(&g_ft_timing, 160); cudaMemset(g_ft_timing, 0, 160); }
+        a.timing = g_ft_timing;
+    }
     static bool configured = false;
     if (!configured) {
         GPP_CUDA_OK(cudaFuncSetAttribute(feature_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));

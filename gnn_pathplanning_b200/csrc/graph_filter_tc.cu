@@ -92,8 +92,16 @@ struct GfTcSmem {
 // the row (conflict-free for row-per-lane writes and for same-row broadcast reads)
 __device__ __forceinline__ int usm_off(int row, int f4) { return row * TC_C + ((f4 ^ (row & 31)) << 2); }
 
+// One arrival per producer WARP (barrier count = 8) and one polling lane per warp: 256 threads arriving on /
+// polling the same mbarrier serialise in the shared-memory atomic unit.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 1) gf_fwd_tc_kernel(const GfT
 
     if (tid == 0) {
         for (int i = 0; i < TC_NA + TC_NB; ++i) mbar_init(&bars[i], 1);
-        for (int i = 0; i < TC_NA + TC_NB; ++i) mbar_init(&fullA[i], TC_THREADS);
+        for (int i = 0; i < TC_NA + TC_NB; ++i) mbar_init(&fullA[i], TC_THREADS / 32);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 1) gf_fwd_tc_kernel(const GfT
         auto issue_b = [&](uint32_t q, int c) {
             const int bs = q % TC_NB;
             const uint32_t use = q / TC_NB;
-            if (use >= 1) mbar_wait(&doneB[bs], (use - 1) & 1);
+            if (use >= 1) mbar_wait_warp(&doneB[bs], (use - 1) & 1);
             const char* src = reinterpret_cast<const char*>(a.wimg) + (size_t)c * TC_STAGE_BYTES;
             const uint32_t dst = smem_u32(sm + L.b_stage(bs));
 #pragma unroll
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 1) gf_fwd_tc_kernel(const GfT
                 if (k == 0) {
                     const int as = ga & 1;
                     const uint32_t ause = ga >> 1;
-                    if (ause >= 1) mbar_wait(&doneA[as], (ause - 1) & 1);
+                    if (ause >= 1) mbar_wait_warp(&doneA[as], (ause - 1) & 1);
                     float4 xv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) xv[i] = xn[i];
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(TC_THREADS + 32, 1) gf_fwd_tc_kernel(const GfT
             // ---- epilogue ---------------------------------------------------------------------------
             {
                 const uint32_t last = gq - 1;
-                mbar_wait(&doneB[last % TC_NB], (last / TC_NB) & 1);     // every MMA of this tile has completed
+                mbar_wait_warp(&doneB[last % TC_NB], (last / TC_NB) & 1);     // every MMA of this tile has completed
                 tcgen05_fence_after();
                 const long long t2 = clock64();
                 const int r = (warp & 3) * 32 + lane;        // TMEM lane = node row of the tile

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256) stage_h2d_kernel(const uint4* __restrict_
 size_t feature_tc_image_floats(int L);
 int launch_prep_feature_tc(const float* w, float* img, int L, cudaStream_t st);
 int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStream_t st);
+int debug_feature_tc_timing(unsigned long long* out20);
 
 // scale = gamma / sqrt(var + eps);  shift = (conv_bias - mean) * scale + beta
 __global__ void fold_bn_kernel(const float* conv_b, const float* g, const float* b, const float* mean,
@@ -205,6 +206,9 @@ extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
     p->gf_mode = mode;
     return GPP_OK;
 }
+
+// debug: per-layer {staging loop, wait for MMAs, epilogue} cycle totals of feature_tc_kernel + tiles at [18]
+extern "C" int gpp_debug_feature_tc_timing(unsigned long long* out20) { return debug_feature_tc_timing(out20); }
 
 extern "C" int gpp_planner_set_feature_mode(gpp_planner* p, int mode) {
     GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_feature_mode: mode must be 0, 1 or 2");
@@ -356,7 +360,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         GPP_CUDA_OK(cudaEventRecord(e0, st));
     }
     int rc;
-    if (p->fe_mode == 2 || (p->fe_mode == 0 && rows >= 256)) {
+    if (p->fe_mode == 2 || (p->fe_mode == 0 && rows >= 4096)) {
         const float* imgs[6];
         for (int l = 0; l < 6; ++l) imgs[l] = A + p->off_fimg[l];
         rc = launch_feature_tc_kernel(fa, imgs, st);

@@ -169,6 +169,9 @@ int gpp_debug_umma_selftest(const float* A, const float* B, float* D, void* stre
 /* Debug: per-phase cycle totals of the tcgen05 filter kernel (filled only when the environment variable
  * GPP_TC_TIMING is set): staging loop, wait for the last MMA, TMEM read-out, propagation, stores, tiles. */
 int gpp_debug_tc_timing(unsigned long long* out6);
+/* Same for the tcgen05 feature extractor: [3*L + {0,1,2}] = layer L staging loop / wait for MMAs / epilogue,
+ * [18] = agent tiles (thread 0 of every CTA). */
+int gpp_debug_feature_tc_timing(unsigned long long* out20);
 
 /* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
  * CUDA events before / between / after its two kernels on the launching stream (at most 8192
