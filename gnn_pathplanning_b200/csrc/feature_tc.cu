@@ -52,7 +52,7 @@ struct FtArgs {
     float* feat;
     int total_agents, apt, num_tiles;
     FtLayer layer[FT_NLAYERS];
-    unsigned long long* timing;    // optional [20] cycle counters (debug): per layer produce / wait / epilogue
+    unsigned long long* timing;    // optional [32] cycle counters (debug): per layer produce / wait / epilogue; [20..] fine
 };
 
 // compile-time layer table
@@ -98,7 +98,7 @@ __device__ __forceinline__ void ft_row_pos(int idx, int& y, int& x) {
 template <int L>
 __device__ __forceinline__ void ft_produce_layer(const FtArgs& A, unsigned char* sm, const float* in_buf, int na,
                                                  uint64_t* doneA, uint64_t* doneB, uint64_t* fullA, uint64_t* fullB,
-                                                 uint32_t& ga, uint32_t& gb, int tid) {
+                                                 uint32_t& ga, uint32_t& gb, int tid, unsigned long long* fine) {
     constexpr int N = ft_n(L), ROWS = ft_rows(L), NK = ft_nk(L), CIN = ft_cin(L), WIN = ft_win(L);
     constexpr int B_BYTES = 2 * N * 128;                 // hi | lo chunk image
     const int ntiles = (na * ROWS + 127) >> 7;
@@ -124,7 +124,9 @@ __device__ __forceinline__ void ft_produce_layer(const FtArgs& A, unsigned char*
         for (int mt = 0; mt < ntiles; ++mt, ++ga) {
             const int as = ga % FT_NA_STAGES;
             const uint32_t ause = ga / FT_NA_STAGES;
+            const long long f0 = clock64();
             if (ause >= 1) ft_mbar_wait_warp(&doneA[as], (ause - 1) & 1);
+            const long long f1 = clock64();
             unsigned char* stage = sm + FT_OFF_A + as * FT_STAGE_BYTES;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -164,8 +166,12 @@ __device__ __forceinline__ void ft_produce_layer(const FtArgs& A, unsigned char*
                 *reinterpret_cast<float4*>(stage + off) = hi;
                 if (L != 0) *reinterpret_cast<float4*>(stage + FT_OP_BYTES + off) = lo;   // conv0 input is exact
             }
+            const long long f2 = clock64();
             fence_proxy_async_smem();
+            const long long f3 = clock64();
             ft_mbar_arrive(&fullA[as]);
+            const long long f4 = clock64();
+            fine[0] += f1 - f0; fine[1] += f2 - f1; fine[2] += f3 - f2; fine[3] += f4 - f3; fine[4] += 1;
             if (mt == 0) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 fence_proxy_async_smem();
@@ -180,7 +186,7 @@ __device__ __forceinline__ void ft_produce_layer(const FtArgs& A, unsigned char*
 template <int L>
 __device__ __forceinline__ void ft_mma_layer(unsigned char* sm, int na, uint32_t tmem_acc, uint64_t* doneA,
                                              uint64_t* doneB, uint64_t* fullA, uint64_t* fullB, uint64_t* layer_done,
-                                             uint32_t& ga, uint32_t& gb) {
+                                             uint32_t& ga, uint32_t& gb, unsigned long long* fine) {
     constexpr int N = ft_n(L), ROWS = ft_rows(L), NK = ft_nk(L);
     constexpr uint32_t IDESC = umma_idesc_tf32(128, N);
     const int ntiles = (na * ROWS + 127) >> 7;
@@ -188,9 +194,11 @@ __device__ __forceinline__ void ft_mma_layer(unsigned char* sm, int na, uint32_t
         const int bs = gb % FT_NB_STAGES;
         for (int mt = 0; mt < ntiles; ++mt, ++ga) {
             const int as = ga % FT_NA_STAGES;
+            const long long m0 = clock64();
             mbar_wait(&fullA[as], (ga / FT_NA_STAGES) & 1);
             if (mt == 0) mbar_wait(&fullB[bs], (gb / FT_NB_STAGES) & 1);
             tcgen05_fence_after();
+            const long long m1 = clock64();
             const uint32_t sa = smem_u32(sm + FT_OFF_A + as * FT_STAGE_BYTES);
             const uint32_t sb = smem_u32(sm + FT_OFF_B + bs * FT_STAGE_BYTES);
             const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + FT_OP_BYTES);
@@ -206,6 +214,8 @@ __device__ __forceinline__ void ft_mma_layer(unsigned char* sm, int na, uint32_t
             for (int ks = 0; ks < 4; ++ks) umma_tf32(acc, a_hi + 2 * ks, b_lo + 2 * ks, IDESC, 1u);
             umma_commit(&doneA[as]);
             if (mt == ntiles - 1) umma_commit(&doneB[bs]);
+            const long long m2 = clock64();
+            fine[0] += m1 - m0; fine[1] += m2 - m1;
         }
         ++gb;
     }
@@ -290,22 +300,24 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
     if (warp == FT_THREADS / 32) {
         // ================= MMA issuer =================
         if (lane == 0) {
+            unsigned long long mfine[2] = {0, 0};
             for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x) {
                 const int na = min(A.apt, A.total_agents - tile * A.apt);
-                ft_mma_layer<0>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb);
-                ft_mma_layer<1>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb);
-                ft_mma_layer<2>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb);
-                ft_mma_layer<3>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb);
-                ft_mma_layer<4>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb);
-                ft_mma_layer<5>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb);
+                ft_mma_layer<0>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb, mfine);
+                ft_mma_layer<1>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb, mfine);
+                ft_mma_layer<2>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb, mfine);
+                ft_mma_layer<3>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb, mfine);
+                ft_mma_layer<4>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb, mfine);
+                ft_mma_layer<5>(sm, na, tmem_acc, doneA, doneB, fullA, fullB, layer_done, ga, gb, mfine);
             }
+            if (A.timing) { atomicAdd(&A.timing[26], mfine[0]); atomicAdd(&A.timing[27], mfine[1]); }
         }
         __syncwarp();
     } else {
         // ================= producers + epilogue =================
         uint32_t nlayer = 0;        // layer_done phases consumed
-        unsigned long long tacc[20];
-        for (int i = 0; i < 20; ++i) tacc[i] = 0;
+        unsigned long long tacc[32];
+        for (int i = 0; i < 32; ++i) tacc[i] = 0;
         for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x) {
             const int a0 = tile * A.apt;
             const int na = min(A.apt, A.total_agents - a0);
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
 #define FT_LAYER(Lx, IN, OUT)                                                                                 \
     {                                                                                                          \
         const long long t0 = clock64();                                                                        \
-        ft_produce_layer<Lx>(A, sm, IN, na, doneA, doneB, fullA, fullB, ga, gb, tid);                          \
+        ft_produce_layer<Lx>(A, sm, IN, na, doneA, doneB, fullA, fullB, ga, gb, tid, tacc + 20);               \
         const long long t1 = clock64();                                                                        \
         ft_mbar_wait_warp(layer_done, nlayer & 1);                                                             \
         ++nlayer;                                                                                              \
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(FT_THREADS + 32, 1) feature_tc_kernel(const Ft
             tacc[18] += 1;
         }
         if (A.timing && tid == 0)
-            for (int i = 0; i < 20; ++i) atomicAdd(&A.timing[i], tacc[i]);
+            for (int i = 0; i < 26; ++i) atomicAdd(&A.timing[i], tacc[i]);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -386,8 +398,8 @@ static unsigned long long* g_ft_timing = nullptr;
 int debug_feature_tc_timing(unsigned long long* out20) {
     if (!g_ft_timing) return GPP_ERR_INVALID;
     cudaDeviceSynchronize();
-    cudaMemcpy(out20, g_ft_timing, 160, cudaMemcpyDeviceToHost);
-    cudaMemset(g_ft_timing, 0, 160);
+    cudaMemcpy(out20, g_ft_timing, 256, cudaMemcpyDeviceToHost);
+    cudaMemset(g_ft_timing, 0, 256);
     return GPP_OK;
 }
 
@@ -417,7 +429,7 @@ int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStr
     a.num_tiles = (fa.total_agents + apt - 1) / apt;
     a.timing = nullptr;
     if (getenv("GPP_TC_TIMING")) {
-        if (!g_ft_timing) { cudaMalloc(&g_ft_timing, 160); cudaMemset(g_ft_timing, 0, 160); }
+        if (!g_ft_timing) { cudaMalloc(&g_ft_timing, 256); cudaMemset(g_ft_timing, 0, 256); }
         a.timing = g_ft_timing;
     }
     static bool configured = false;
