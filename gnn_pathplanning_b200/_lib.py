@@ -14,7 +14,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgnnpp_b200.so")
-SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "feature.cu", "feature_tc.cu", "planner.cu")
+SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "feature.cu", "feature_tc.cu", "train.cu", "planner.cu")
 HEADERS = ("common.cuh", "feature.cuh", "tc_common.cuh")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200.h")
 
@@ -36,6 +36,7 @@ EXPORTED = (
     "gpp_graph_filter_backward_workspace_bytes", "gpp_graph_filter_backward",
     "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
     "gpp_planner_forward", "gpp_planner_forward_host",
+    "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward",
     "gpp_planner_forward_host_async", "gpp_planner_wait", "gpp_debug_tc_timing", "gpp_debug_feature_tc_timing",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
     "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode", "gpp_debug_umma_selftest",
@@ -48,6 +49,20 @@ class PlannerWeights(C.Structure):
         ("conv_w", C.c_void_p * 5), ("conv_b", C.c_void_p * 5),
         ("bn_w", C.c_void_p * 5), ("bn_b", C.c_void_p * 5),
         ("bn_mean", C.c_void_p * 5), ("bn_var", C.c_void_p * 5),
+        ("compress_w", C.c_void_p), ("compress_b", C.c_void_p),
+        ("gf_w", C.c_void_p), ("gf_b", C.c_void_p),
+        ("action_w", C.c_void_p), ("action_b", C.c_void_p),
+    ]
+
+
+class PlannerBnState(C.Structure):
+    _fields_ = [("running_mean", C.c_void_p * 5), ("running_var", C.c_void_p * 5)]
+
+
+class PlannerGrads(C.Structure):
+    _fields_ = [
+        ("conv_w", C.c_void_p * 5), ("conv_b", C.c_void_p * 5),
+        ("bn_w", C.c_void_p * 5), ("bn_b", C.c_void_p * 5),
         ("compress_w", C.c_void_p), ("compress_b", C.c_void_p),
         ("gf_w", C.c_void_p), ("gf_b", C.c_void_p),
         ("action_w", C.c_void_p), ("action_b", C.c_void_p),
@@ -118,6 +133,14 @@ def load():
         lib.gpp_planner_forward.argtypes = [vp, vp, vp, i, vp, vp, i, i, vp]
         lib.gpp_planner_forward_host.restype = i
         lib.gpp_planner_forward_host.argtypes = [vp, vp, vp, i, vp, i, i]
+        lib.gpp_planner_train_workspace_bytes.restype = sz
+        lib.gpp_planner_train_workspace_bytes.argtypes = [i, i, i]
+        lib.gpp_planner_train_forward.restype = i
+        lib.gpp_planner_train_forward.argtypes = [C.POINTER(PlannerWeights), C.POINTER(PlannerBnState), C.c_float,
+                                                  vp, vp, i, vp, vp, i, i, i, vp]
+        lib.gpp_planner_train_backward.restype = i
+        lib.gpp_planner_train_backward.argtypes = [C.POINTER(PlannerWeights), vp, vp, i, vp, vp,
+                                                   C.POINTER(PlannerGrads), i, i, i, vp]
         lib.gpp_planner_forward_host_async.restype = i
         lib.gpp_planner_forward_host_async.argtypes = [vp, vp, vp, i, vp, i, i, C.POINTER(C.c_ulonglong)]
         lib.gpp_planner_wait.restype = i

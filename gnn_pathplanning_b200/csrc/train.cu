@@ -1,0 +1,599 @@
+// Training-mode forward and backward of the whole planner for sm_100a (fp32 CUDA cores).
+//
+// Replaces, in train mode, DecentralPlannerNet.forward (/root/reference/graphs/models/decentralplanner.py
+// :278-318) and the autograd pass behind `loss.backward()` (/root/reference/agents/decentralplannerlocal.py
+// :297-314).  The reference calls ConvLayers once PER AGENT, so its BatchNorm batch statistics are taken over
+// (B,H,W) of one agent's slice and the running statistics are updated N times per forward, in agent order;
+// both are reproduced exactly here with all B*N agents batched (image index = b*N + n).
+//
+// Everything is a plain data-parallel kernel with fixed-order reductions (deterministic gradients); the graph
+// filter forward/backward reuse the fused kernels of graph_filter.cu through the C ABI entry points.
+#include "common.cuh"
+
+namespace gpp {
+
+static const int kC[6] = {3, 32, 32, 64, 64, 128};     // channels
+static const int kH[5] = {11, 5, 5, 2, 2};             // conv input = output height/width of layer l
+static inline bool pooled_after(int l) { return l == 0 || l == 2 || l == 4; }
+static inline int pooled_hw(int l) { return kH[l] / 2; }
+
+// ---------------------------------------------------------------------------------------
+// forward kernels
+// ---------------------------------------------------------------------------------------
+// out[img][co][y][x] = b[co] + sum_{ci,ky,kx} in[img][ci][y+ky-1][x+kx-1] w[co][ci][ky][kx]   (3x3, pad 1)
+__global__ void conv3x3_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                   const float* __restrict__ b, float* __restrict__ out, int M, int Cin, int Cout,
+                                   int H) {
+    const int HW = H * H;
+    const long long total = (long long)M * Cout * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int pos = (int)(i % HW), co = (int)((i / HW) % Cout);
+        const long long img = i / ((long long)HW * Cout);
+        const int y = pos / H, x = pos - y * H;
+        float acc = b[co];
+        const float* ip = in + img * Cin * HW;
+        const float* wp = w + (size_t)co * Cin * 9;
+        for (int ci = 0; ci < Cin; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = y + ky - 1;
+                if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = x + kx - 1;
+                    if (ix < 0 || ix >= H) continue;
+                    acc = fmaf(ip[ci * HW + iy * H + ix], wp[ci * 9 + ky * 3 + kx], acc);
+                }
+            }
+        }
+        out[i] = acc;
+    }
+}
+
+// block reduction of two doubles
+__device__ __forceinline__ void block_reduce2(double& a, double& b) {
+    __shared__ double sa[32], sb[32];
+    for (int off = 16; off > 0; off >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        a = lane < nw ? sa[lane] : 0.0;
+        b = lane < nw ? sb[lane] : 0.0;
+        for (int off = 16; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off);
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+        }
+        if (lane == 0) { sa[0] = a; sb[0] = b; }
+    }
+    __syncthreads();
+    a = sa[0];
+    b = sb[0];
+    __syncthreads();
+}
+
+// per (agent n, channel c): mean and biased variance over (b, y, x) of z[(b*N+n)][c][:]; one CTA per group
+__global__ void bn_stats_kernel(const float* __restrict__ z, float* __restrict__ mean, float* __restrict__ var,
+                                float* __restrict__ invstd, int B, int N, int C, int HW, float eps) {
+    const int n = blockIdx.x / C, c = blockIdx.x - n * C;
+    const int cnt = B * HW;
+    double s = 0.0, q = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b = i / HW, p = i - b * HW;
+        s += (double)z[((size_t)(b * N + n) * C + c) * HW + p];
+    }
+    block_reduce2(s, q);
+    const double mu = s / cnt;
+    double d2 = 0.0, zero = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b = i / HW, p = i - b * HW;
+        const double d = (double)z[((size_t)(b * N + n) * C + c) * HW + p] - mu;
+        d2 += d * d;
+    }
+    block_reduce2(d2, zero);
+    if (threadIdx.x == 0) {
+        const float v = (float)(d2 / cnt);
+        mean[blockIdx.x] = (float)mu;
+        var[blockIdx.x] = v;
+        invstd[blockIdx.x] = 1.0f / sqrtf(v + eps);
+    }
+}
+
+// a = relu(gamma * (z - mean) * invstd + beta)
+__global__ void bn_apply_relu_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float* __restrict__ a, long long total, int N,
+                                     int C, int HW) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / HW) % C);
+        const int n = (int)((i / ((long long)HW * C)) % N);
+        const int g = n * C + c;
+        a[i] = fmaxf(fmaf((z[i] - mean[g]) * invstd[g], gamma[c], beta[c]), 0.f);
+    }
+}
+
+// running <- (1-m) running + m stat_n, n = 0..N-1 in agent order (unbiased variance for running_var)
+__global__ void bn_running_kernel(const float* __restrict__ mean, const float* __restrict__ var, float* rm, float* rv,
+                                  int N, int C, int cnt, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float m = rm[c], v = rv[c];
+    const float unb = cnt > 1 ? (float)cnt / (float)(cnt - 1) : 1.f;
+    for (int n = 0; n < N; ++n) {
+        m = (1.f - momentum) * m + momentum * mean[n * C + c];
+        v = (1.f - momentum) * v + momentum * (var[n * C + c] * unb);
+    }
+    rm[c] = m;
+    rv[c] = v;
+}
+
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ a, float* __restrict__ p, long long total, int H, int Hp) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int px = (int)(i % Hp), py = (int)((i / Hp) % Hp);
+        const long long plane = i / (Hp * Hp);
+        const float* ap = a + plane * H * H + (2 * py) * H + 2 * px;
+        p[i] = fmaxf(fmaxf(ap[0], ap[1]), fmaxf(ap[H], ap[H + 1]));
+    }
+}
+
+// out[r][o] = act(b[o] + sum_i in[r][i] w[o][i])
+__global__ void linear_fwd_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ b,
+                                  float* __restrict__ out, long long R, int I, int O, int relu) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R * O; i += (long long)gridDim.x * blockDim.x) {
+        const int o = (int)(i % O);
+        const long long r = i / O;
+        float acc = b[o];
+        const float* ip = in + r * I;
+        const float* wp = w + (size_t)o * I;
+        for (int k = 0; k < I; ++k) acc = fmaf(ip[k], wp[k], acc);
+        out[i] = relu ? fmaxf(acc, 0.f) : acc;
+    }
+}
+
+// logits[n][b][a] = ba[a] + sum_f shared[(b*N+n)][f] wa[a][f]
+__global__ void action_fwd_kernel(const float* __restrict__ shared, const float* __restrict__ wa,
+                                  const float* __restrict__ ba, float* __restrict__ logits, int B, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N * 5) return;
+    const int a = i % 5, r = i / 5, b = r / N, n = r - b * N;
+    float acc = ba[a];
+    for (int f = 0; f < 128; ++f) acc = fmaf(shared[(size_t)r * 128 + f], wa[a * 128 + f], acc);
+    logits[((size_t)n * B + b) * 5 + a] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// backward kernels
+// ---------------------------------------------------------------------------------------
+// dshared[r][f] = sum_a dlogits[n][b][a] wa[a][f]
+__global__ void action_bwd_input_kernel(const float* __restrict__ dlogits, const float* __restrict__ wa,
+                                        float* __restrict__ dshared, int B, int N) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N * 128) return;
+    const int f = (int)(i % 128);
+    const long long r = i / 128;
+    const int b = (int)(r / N), n = (int)(r - (long long)b * N);
+    const float* dl = dlogits + ((size_t)n * B + b) * 5;
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) acc = fmaf(dl[a], wa[a * 128 + f], acc);
+    dshared[i] = acc;
+}
+// dwa[a][f] = sum_r dlogits[r][a] shared[r][f] ; dba[a] = sum_r dlogits[r][a]   (thread per (a,f), one extra per a)
+__global__ void action_bwd_weight_kernel(const float* __restrict__ dlogits, const float* __restrict__ shared,
+                                         float* __restrict__ dwa, float* __restrict__ dba, int B, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 5 * 128) {
+        const int a = i / 128, f = i - a * 128;
+        double acc = 0.0;
+        for (int b = 0; b < B; ++b)
+            for (int n = 0; n < N; ++n)
+                acc += (double)(dlogits[((size_t)n * B + b) * 5 + a] * shared[((size_t)b * N + n) * 128 + f]);
+        dwa[i] = (float)acc;
+    } else if (i < 5 * 128 + 5) {
+        const int a = i - 5 * 128;
+        double acc = 0.0;
+        for (int b = 0; b < B; ++b)
+            for (int n = 0; n < N; ++n) acc += (double)dlogits[((size_t)n * B + b) * 5 + a];
+        dba[a] = (float)acc;
+    }
+}
+
+// g[i] *= (y[i] > 0)
+__global__ void relu_mask_kernel(float* __restrict__ g, const float* __restrict__ y, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        if (!(y[i] > 0.f)) g[i] = 0.f;
+}
+
+// din[r][i] = sum_o dout[r][o] w[o][i]
+__global__ void linear_bwd_input_kernel(const float* __restrict__ dout, const float* __restrict__ w,
+                                        float* __restrict__ din, long long R, int I, int O) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < R * I; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % I);
+        const long long r = i / I;
+        float acc = 0.f;
+        for (int o = 0; o < O; ++o) acc = fmaf(dout[r * O + o], w[(size_t)o * I + k], acc);
+        din[i] = acc;
+    }
+}
+// partial[chunk][o][i] = sum_{r in chunk} dout[r][o] in[r][i] ; partial_b[chunk][o] = sum dout[r][o]
+__global__ void linear_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ in,
+                                         float* __restrict__ partial, float* __restrict__ partial_b, long long R, int I,
+                                         int O, int rows_per_chunk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = r0 + rows_per_chunk < R ? r0 + rows_per_chunk : R;
+    if (i < O * I) {
+        const int o = i / I, k = i - o * I;
+        double acc = 0.0;
+        for (long long r = r0; r < r1; ++r) acc += (double)(dout[r * O + o] * in[r * I + k]);
+        partial[(size_t)blockIdx.y * O * I + i] = (float)acc;
+    } else if (i < O * I + O) {
+        const int o = i - O * I;
+        double acc = 0.0;
+        for (long long r = r0; r < r1; ++r) acc += (double)dout[r * O + o];
+        partial_b[(size_t)blockIdx.y * O + o] = (float)acc;
+    }
+}
+__global__ void reduce_chunks_kernel(const float* __restrict__ partial, float* __restrict__ out, int chunks, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += (double)partial[(size_t)c * n + i];
+    out[i] = (float)s;
+}
+
+// da[plane][y][x] = dp[plane][y/2][x/2] if (y,x) is the (first) arg-max of its 2x2 window, else 0
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ a, const float* __restrict__ dp, float* __restrict__ da,
+                                    long long total, int H, int Hp) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % H), y = (int)((i / H) % H);
+        const long long plane = i / (H * H);
+        const int py = y >> 1, px = x >> 1;
+        float g = 0.f;
+        if (py < Hp && px < Hp) {
+            const float* ap = a + plane * H * H + (2 * py) * H + 2 * px;
+            const float v[4] = {ap[0], ap[1], ap[H], ap[H + 1]};
+            int best = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (v[k] > v[best]) best = k;
+            if (best == (y & 1) * 2 + (x & 1)) g = dp[plane * Hp * Hp + py * Hp + px];
+        }
+        da[i] = g;
+    }
+}
+
+// per (n,c): s1 = sum dy_eff, s2 = sum dy_eff * xhat, dy_eff = da * (a > 0), xhat = (z - mean) * invstd
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ a,
+                                     const float* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, double* __restrict__ s1, double* __restrict__ s2,
+                                     int B, int N, int C, int HW) {
+    const int n = blockIdx.x / C, c = blockIdx.x - n * C;
+    const int cnt = B * HW;
+    const float mu = mean[blockIdx.x], is = invstd[blockIdx.x];
+    double t1 = 0.0, t2 = 0.0;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b = i / HW, p = i - b * HW;
+        const size_t idx = ((size_t)(b * N + n) * C + c) * HW + p;
+        const float dy = a[idx] > 0.f ? da[idx] : 0.f;
+        t1 += (double)dy;
+        t2 += (double)dy * (((double)z[idx] - (double)mu) * (double)is);
+    }
+    block_reduce2(t1, t2);
+    if (threadIdx.x == 0) {
+        s1[blockIdx.x] = t1;
+        s2[blockIdx.x] = t2;
+    }
+}
+// dgamma[c] = sum_n s2[n][c], dbeta[c] = sum_n s1[n][c]
+__global__ void bn_param_grad_kernel(const double* __restrict__ s1, const double* __restrict__ s2, float* dgamma,
+                                     float* dbeta, int N, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double g = 0.0, b = 0.0;
+    for (int n = 0; n < N; ++n) {
+        g += s2[n * C + c];
+        b += s1[n * C + c];
+    }
+    dgamma[c] = (float)g;
+    dbeta[c] = (float)b;
+}
+// dz = gamma * invstd * (dy_eff - s1/m - xhat * s2/m)     (written in place over da)
+__global__ void bn_bwd_apply_kernel(float* __restrict__ da, const float* __restrict__ a, const float* __restrict__ z,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const double* __restrict__ s1,
+                                    const double* __restrict__ s2, long long total, int B, int N, int C, int HW) {
+    // evaluated in double like the reference's CPU kernel (its accumulate type for float is double): for
+    // (agent, channel) groups with near-zero variance invstd is ~316 and dy - mean(dy) cancels almost exactly
+    const double inv_m = 1.0 / (double)(B * HW);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / HW) % C);
+        const int n = (int)((i / ((long long)HW * C)) % N);
+        const int g = n * C + c;
+        const double dy = a[i] > 0.f ? (double)da[i] : 0.0;
+        const double is = (double)invstd[g];
+        const double xhat = ((double)z[i] - (double)mean[g]) * is;
+        da[i] = (float)((double)gamma[c] * is * (dy - s1[g] * inv_m - xhat * s2[g] * inv_m));
+    }
+}
+
+// din[img][ci][y][x] = sum_{co,ky,kx} dz[img][co][y+1-ky][x+1-kx] w[co][ci][ky][kx]
+__global__ void conv3x3_bwd_input_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                         float* __restrict__ din, int M, int Cin, int Cout, int H) {
+    const int HW = H * H;
+    const long long total = (long long)M * Cin * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int pos = (int)(i % HW), ci = (int)((i / HW) % Cin);
+        const long long img = i / ((long long)HW * Cin);
+        const int y = pos / H, x = pos - y * H;
+        float acc = 0.f;
+        const float* dp = dz + img * Cout * HW;
+        for (int co = 0; co < Cout; ++co) {
+            const float* wp = w + ((size_t)co * Cin + ci) * 9;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int oy = y + 1 - ky;
+                if (oy < 0 || oy >= H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ox = x + 1 - kx;
+                    if (ox < 0 || ox >= H) continue;
+                    acc = fmaf(dp[co * HW + oy * H + ox], wp[ky * 3 + kx], acc);
+                }
+            }
+        }
+        din[i] = acc;
+    }
+}
+// partial[chunk][co][ci][tap] = sum_{img in chunk, pos} dz[img][co][pos] in[img][ci][pos + tap - 1]
+// partial_b[chunk][co] = sum dz[img][co][pos]                                  (one extra thread per co)
+__global__ void conv3x3_bwd_weight_kernel(const float* __restrict__ dz, const float* __restrict__ in,
+                                          float* __restrict__ partial, float* __restrict__ partial_b, int M, int Cin,
+                                          int Cout, int H, int imgs_per_chunk) {
+    const int HW = H * H;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = blockIdx.y * imgs_per_chunk;
+    const int m1 = min(M, m0 + imgs_per_chunk);
+    const int nW = Cout * Cin * 9;
+    if (i < nW) {
+        const int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+        const int ky = tap / 3, kx = tap - ky * 3;
+        // weight gradients are long sums with heavy cancellation: per-image fp32 dot products, fp64 across images
+        double acc = 0.0;
+        for (int img = m0; img < m1; ++img) {
+            const float* dp = dz + ((size_t)img * Cout + co) * HW;
+            const float* ip = in + ((size_t)img * Cin + ci) * HW;
+            float t = 0.f;
+            for (int y = 0; y < H; ++y) {
+                const int iy = y + ky - 1;
+                if (iy < 0 || iy >= H) continue;
+                for (int x = 0; x < H; ++x) {
+                    const int ix = x + kx - 1;
+                    if (ix < 0 || ix >= H) continue;
+                    t = fmaf(dp[y * H + x], ip[iy * H + ix], t);
+                }
+            }
+            acc += (double)t;
+        }
+        partial[(size_t)blockIdx.y * nW + i] = (float)acc;
+    } else if (i < nW + Cout) {
+        const int co = i - nW;
+        double acc = 0.0;
+        for (int img = m0; img < m1; ++img) {
+            const float* dp = dz + ((size_t)img * Cout + co) * HW;
+            for (int p = 0; p < HW; ++p) acc += (double)dp[p];
+        }
+        partial_b[(size_t)blockIdx.y * Cout + co] = (float)acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------
+struct TrainWs {
+    size_t z[5], a[5], p[5], mean[5], var[5], invstd[5], s1, s2;
+    size_t feat, shared, dfeat, dshared, dbuf0, dbuf1, partial, partial_b, gf_fwd, gf_bwd, total;
+    int chunks;
+};
+static TrainWs train_layout(int B, int N, int K) {
+    TrainWs L;
+    const size_t M = (size_t)B * N;
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
+    size_t maxact = 0;
+    for (int l = 0; l < 5; ++l) {
+        const size_t n = M * kC[l + 1] * kH[l] * kH[l];
+        L.z[l] = take(n);
+        L.a[l] = take(n);
+        L.p[l] = pooled_after(l) ? take(M * kC[l + 1] * pooled_hw(l) * pooled_hw(l)) : 0;
+        L.mean[l] = take((size_t)N * kC[l + 1]);
+        L.var[l] = take((size_t)N * kC[l + 1]);
+        L.invstd[l] = take((size_t)N * kC[l + 1]);
+        if (n > maxact) maxact = n;
+    }
+    L.s1 = take((size_t)N * 128 * 2);      // doubles
+    L.s2 = take((size_t)N * 128 * 2);
+    L.feat = take(M * 128);
+    L.shared = take(M * 128);
+    L.dfeat = take(M * 128);
+    L.dshared = take(M * 128);
+    L.dbuf0 = take(maxact);
+    L.dbuf1 = take(maxact);
+    L.chunks = (int)(M < 64 ? M : 64);
+    L.partial = take((size_t)L.chunks * 128 * 64 * 9);
+    L.partial_b = take((size_t)L.chunks * 128);
+    L.gf_fwd = take(gpp_graph_filter_workspace_bytes(128, 128, K) / 4 + 64);
+    L.gf_bwd = take(gpp_graph_filter_backward_workspace_bytes(B, N, 128, 128, K) / 4 + 64);
+    L.total = off;
+    return L;
+}
+
+static inline int grid_for(long long total, int block = 256) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace gpp
+
+using namespace gpp;
+
+extern "C" size_t gpp_planner_train_workspace_bytes(int B, int N, int K) {
+    if (B <= 0 || N <= 0 || K <= 0) return 0;
+    return train_layout(B, N, K).total * sizeof(float);
+}
+
+extern "C" int gpp_planner_train_forward(const gpp_planner_weights* w, const gpp_planner_bn_state* bn, float momentum,
+                                         const float* x, const void* S, int s_is_f64, float* logits, void* workspace,
+                                         int B, int N, int K, void* stream) {
+    GPP_REQUIRE(w && x && S && logits && workspace, GPP_ERR_INVALID, "planner_train_forward: null pointer");
+    GPP_REQUIRE(B >= 1 && N >= 1 && N <= 64 && K >= 1, GPP_ERR_INVALID, "planner_train_forward: bad sizes B=%d N=%d K=%d", B, N, K);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const TrainWs L = train_layout(B, N, K);
+    float* ws = reinterpret_cast<float*>(workspace);
+    const int M = B * N;
+    const float* in = x;
+    for (int l = 0; l < 5; ++l) {
+        const int Cin = kC[l], Cout = kC[l + 1], H = kH[l], HW = H * H;
+        const long long total = (long long)M * Cout * HW;
+        float* z = ws + L.z[l];
+        float* a = ws + L.a[l];
+        conv3x3_fwd_kernel<<<grid_for(total), 256, 0, st>>>(in, w->conv_w[l], w->conv_b[l], z, M, Cin, Cout, H);
+        GPP_LAUNCH_CHECK();
+        bn_stats_kernel<<<N * Cout, 128, 0, st>>>(z, ws + L.mean[l], ws + L.var[l], ws + L.invstd[l], B, N, Cout, HW, 1e-5f);
+        GPP_LAUNCH_CHECK();
+        bn_apply_relu_kernel<<<grid_for(total), 256, 0, st>>>(z, ws + L.mean[l], ws + L.invstd[l], w->bn_w[l], w->bn_b[l],
+                                                              a, total, N, Cout, HW);
+        GPP_LAUNCH_CHECK();
+        if (bn && bn->running_mean[l] && bn->running_var[l]) {
+            bn_running_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(ws + L.mean[l], ws + L.var[l], bn->running_mean[l],
+                                                                  bn->running_var[l], N, Cout, B * HW, momentum);
+            GPP_LAUNCH_CHECK();
+        }
+        if (pooled_after(l)) {
+            const int Hp = pooled_hw(l);
+            const long long tp = (long long)M * Cout * Hp * Hp;
+            maxpool2_fwd_kernel<<<grid_for(tp), 256, 0, st>>>(a, ws + L.p[l], tp, H, Hp);
+            GPP_LAUNCH_CHECK();
+            in = ws + L.p[l];
+        } else {
+            in = a;
+        }
+    }
+    linear_fwd_kernel<<<grid_for((long long)M * 128), 256, 0, st>>>(in, w->compress_w, w->compress_b, ws + L.feat, M, 128, 128, 1);
+    GPP_LAUNCH_CHECK();
+    int rc = gpp_graph_filter_forward(ws + L.feat, S, s_is_f64, w->gf_w, w->gf_b, ws + L.shared, B, N, 128, 128, K,
+                                      GPP_NODE_MAJOR, GPP_NODE_MAJOR, 1, ws + L.gf_fwd, stream);
+    if (rc) return rc;
+    action_fwd_kernel<<<(M * 5 + 255) / 256, 256, 0, st>>>(ws + L.shared, w->action_w, w->action_b, logits, B, N);
+    GPP_LAUNCH_CHECK();
+    return GPP_OK;
+}
+
+extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const float* x, const void* S, int s_is_f64,
+                                          const float* dlogits, void* workspace, const gpp_planner_grads* g, int B,
+                                          int N, int K, void* stream) {
+    GPP_REQUIRE(w && x && S && dlogits && workspace && g, GPP_ERR_INVALID, "planner_train_backward: null pointer");
+    GPP_REQUIRE(B >= 1 && N >= 1 && N <= 64 && K >= 1, GPP_ERR_INVALID, "planner_train_backward: bad sizes");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const TrainWs L = train_layout(B, N, K);
+    float* ws = reinterpret_cast<float*>(workspace);
+    const int M = B * N;
+    // ---- action MLP
+    action_bwd_input_kernel<<<grid_for((long long)M * 128), 256, 0, st>>>(dlogits, w->action_w, ws + L.dshared, B, N);
+    GPP_LAUNCH_CHECK();
+    action_bwd_weight_kernel<<<(5 * 128 + 5 + 127) / 128, 128, 0, st>>>(dlogits, ws + L.shared, g->action_w, g->action_b, B, N);
+    GPP_LAUNCH_CHECK();
+    // ---- graph filter (+ReLU): fused kernels
+    int rc = gpp_graph_filter_backward(ws + L.dshared, ws + L.shared, ws + L.feat, S, s_is_f64, w->gf_w, ws + L.dfeat,
+                                       g->gf_w, g->gf_b, B, N, 128, 128, K, GPP_NODE_MAJOR, GPP_NODE_MAJOR, 1,
+                                       ws + L.gf_bwd, stream);
+    if (rc) return rc;
+    // ---- compress MLP (+ReLU)
+    const float* lin_in = ws + L.p[4];
+    relu_mask_kernel<<<grid_for((long long)M * 128), 256, 0, st>>>(ws + L.dfeat, ws + L.feat, (long long)M * 128);
+    GPP_LAUNCH_CHECK();
+    {
+        const int rpc = (M + L.chunks - 1) / L.chunks;
+        const int used = (M + rpc - 1) / rpc;
+        linear_bwd_weight_kernel<<<dim3((128 * 128 + 128 + 255) / 256, used), 256, 0, st>>>(
+            ws + L.dfeat, lin_in, ws + L.partial, ws + L.partial_b, M, 128, 128, rpc);
+        GPP_LAUNCH_CHECK();
+        reduce_chunks_kernel<<<(128 * 128 + 255) / 256, 256, 0, st>>>(ws + L.partial, g->compress_w, used, 128 * 128);
+        GPP_LAUNCH_CHECK();
+        reduce_chunks_kernel<<<1, 128, 0, st>>>(ws + L.partial_b, g->compress_b, used, 128);
+        GPP_LAUNCH_CHECK();
+    }
+    float* dcur = ws + L.dbuf0;      // gradient w.r.t. the current layer's output (post-pool if pooled)
+    float* dnext = ws + L.dbuf1;
+    linear_bwd_input_kernel<<<grid_for((long long)M * 128), 256, 0, st>>>(ws + L.dfeat, w->compress_w, dcur, M, 128, 128);
+    GPP_LAUNCH_CHECK();
+    // ---- conv stack, last layer first
+    for (int l = 4; l >= 0; --l) {
+        const int Cin = kC[l], Cout = kC[l + 1], H = kH[l], HW = H * H;
+        const long long total = (long long)M * Cout * HW;
+        const float* z = ws + L.z[l];
+        const float* a = ws + L.a[l];
+        float* da = dcur;
+        if (pooled_after(l)) {
+            const int Hp = pooled_hw(l);
+            maxpool2_bwd_kernel<<<grid_for(total), 256, 0, st>>>(a, dcur, dnext, total, H, Hp);
+            GPP_LAUNCH_CHECK();
+            da = dnext;
+            float* t = dcur; dcur = dnext; dnext = t;
+        }
+        double* s1 = reinterpret_cast<double*>(ws + L.s1);
+        double* s2 = reinterpret_cast<double*>(ws + L.s2);
+        bn_bwd_reduce_kernel<<<N * Cout, 128, 0, st>>>(da, a, z, ws + L.mean[l], ws + L.invstd[l], s1, s2, B, N, Cout, HW);
+        GPP_LAUNCH_CHECK();
+        bn_param_grad_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(s1, s2, g->bn_w[l], g->bn_b[l], N, Cout);
+        GPP_LAUNCH_CHECK();
+        bn_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(da, a, z, ws + L.mean[l], ws + L.invstd[l], w->bn_w[l],
+                                                             s1, s2, total, B, N, Cout, HW);
+        GPP_LAUNCH_CHECK();
+        // da now holds dz
+        const float* lin = (l == 0) ? x : (pooled_after(l - 1) ? ws + L.p[l - 1] : ws + L.a[l - 1]);
+        {
+            const int ipc = (M + L.chunks - 1) / L.chunks;
+            const int used = (M + ipc - 1) / ipc;
+            const int nW = Cout * Cin * 9;
+            conv3x3_bwd_weight_kernel<<<dim3((nW + Cout + 255) / 256, used), 256, 0, st>>>(da, lin, ws + L.partial, ws + L.partial_b,
+                                                                                        M, Cin, Cout, H, ipc);
+            GPP_LAUNCH_CHECK();
+            reduce_chunks_kernel<<<(nW + 255) / 256, 256, 0, st>>>(ws + L.partial, g->conv_w[l], used, nW);
+            GPP_LAUNCH_CHECK();
+            reduce_chunks_kernel<<<1, 128, 0, st>>>(ws + L.partial_b, g->conv_b[l], used, Cout);
+            GPP_LAUNCH_CHECK();
+        }
+        if (l > 0) {
+            conv3x3_bwd_input_kernel<<<grid_for((long long)M * Cin * HW), 256, 0, st>>>(da, w->conv_w[l], dnext, M, Cin, Cout, H);
+            GPP_LAUNCH_CHECK();
+            float* t = dcur; dcur = dnext; dnext = t;
+        }
+    }
+    return GPP_OK;
+}
+
+// debug: single training kernels for unit tests (tests/ only)
+//   op 0: conv3x3_fwd (a = in, b = w, c = bias)      op 1: conv3x3_bwd_input (a = dz, b = w)
+//   op 2: maxpool2_bwd (a = act, b = dp)
+extern "C" int gpp_debug_train_kernel(int op, const float* a, const float* b, const float* c, float* out, int M,
+                                      int Cin, int Cout, int H, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (op == 0) {
+        conv3x3_fwd_kernel<<<grid_for((long long)M * Cout * H * H), 256, 0, st>>>(a, b, c, out, M, Cin, Cout, H);
+    } else if (op == 1) {
+        conv3x3_bwd_input_kernel<<<grid_for((long long)M * Cin * H * H), 256, 0, st>>>(a, b, out, M, Cin, Cout, H);
+    } else if (op == 2) {
+        const long long total = (long long)M * Cout * H * H;
+        maxpool2_bwd_kernel<<<grid_for(total), 256, 0, st>>>(a, b, out, total, H, H / 2);
+    } else {
+        set_error("debug_train_kernel: unknown op %d", op);
+        return GPP_ERR_INVALID;
+    }
+    GPP_LAUNCH_CHECK();
+    return GPP_OK;
+}

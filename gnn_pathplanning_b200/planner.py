@@ -11,10 +11,11 @@ Execution:
   * eval mode under torch.no_grad()  -> gpp_planner_forward: two kernels (agent-tiled
     CNN+compress feature extractor; fused graph filter + ReLU + action MLP), logits
     written agent-major so the returned list is N views of one buffer.
-  * otherwise (training / autograd)   -> agents batched into one [B*N,...] pass per layer
-    with the reference's PER-AGENT BatchNorm statistics and sequential running-stat
-    updates reproduced exactly, and the fused graph-filter kernels (forward + backward)
-    through torch.autograd.
+  * train mode                        -> gpp_planner_train_forward / _backward (one
+    torch.autograd.Function around the whole network): all B*N agents batched, the
+    reference's PER-AGENT BatchNorm statistics and N sequential running-stat updates
+    reproduced exactly, deterministic fixed-order gradient reductions.
+  * eval mode under autograd (rare)   -> batched torch ops + the fused graph-filter kernels.
 CUDA only: the module raises if asked to run on CPU tensors.
 """
 from __future__ import annotations
@@ -69,6 +70,87 @@ class _Conv3x3Fp32(torch.autograd.Function):
                 gy.contiguous(), x, w, [w.shape[0]], [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
                 [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
         return gx, gw, gb
+
+
+class _PlannerTrainFn(torch.autograd.Function):
+    """Train-mode forward/backward of the whole planner in the library's own kernels
+    (gpp_planner_train_forward / _backward): conv + per-agent BatchNorm + ReLU + max-pool stack,
+    compress MLP, fused graph filter, action MLP.  Parameter order = _train_params()."""
+
+    @staticmethod
+    def forward(ctx, module, x, S, *params):
+        lib = _lib.load()
+        B, N = x.shape[0], x.shape[1]
+        K = module.K[0]
+        x = x.contiguous().float()
+        S3 = S[:, 0] if S.dim() == 4 else S
+        if S3.dtype not in (torch.float32, torch.float64):
+            S3 = S3.float()
+        S3 = S3.contiguous()
+        params = [p.contiguous() for p in params]
+        w = _fill_weights(params, module)
+        bn = _lib.PlannerBnState()
+        momentum = 0.1
+        for l, ci in enumerate(_CONV_IDX):
+            b = module.ConvLayers[ci + 1]
+            if b.track_running_stats and b.running_mean is not None:
+                bn.running_mean[l] = b.running_mean.data_ptr()
+                bn.running_var[l] = b.running_var.data_ptr()
+                momentum = b.momentum
+        ws = torch.empty(lib.gpp_planner_train_workspace_bytes(B, N, K) // 4 + 16, device=x.device, dtype=torch.float32)
+        logits = torch.empty(N, B, 5, device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.gpp_planner_train_forward(C.byref(w), C.byref(bn), momentum, x.data_ptr(), S3.data_ptr(),
+                                                 int(S3.dtype == torch.float64), logits.data_ptr(), ws.data_ptr(),
+                                                 B, N, K, stream))
+        with torch.no_grad():
+            for ci in _CONV_IDX:
+                b = module.ConvLayers[ci + 1]
+                if b.track_running_stats and b.num_batches_tracked is not None:
+                    b.num_batches_tracked += N          # one update per agent call in the reference
+        ctx.module = module
+        ctx.save_for_backward(x, S3, ws, *params)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.load()
+        x, S3, ws, *params = ctx.saved_tensors
+        module = ctx.module
+        B, N = x.shape[0], x.shape[1]
+        w = _fill_weights(params, module)
+        grads = [torch.empty_like(p) for p in params]
+        g = _lib.PlannerGrads()
+        for l in range(5):
+            g.conv_w[l] = grads[l].data_ptr()
+            g.conv_b[l] = grads[5 + l].data_ptr()
+            g.bn_w[l] = grads[10 + l].data_ptr()
+            g.bn_b[l] = grads[15 + l].data_ptr()
+        g.compress_w, g.compress_b = grads[20].data_ptr(), grads[21].data_ptr()
+        g.gf_w, g.gf_b = grads[22].data_ptr(), grads[23].data_ptr()
+        g.action_w, g.action_b = grads[24].data_ptr(), grads[25].data_ptr()
+        dl = dlogits.contiguous()
+        _lib.check(lib.gpp_planner_train_backward(C.byref(w), x.data_ptr(), S3.data_ptr(), int(S3.dtype == torch.float64),
+                                                  dl.data_ptr(), ws.data_ptr(), C.byref(g), B, N, module.K[0],
+                                                  torch.cuda.current_stream().cuda_stream))
+        return (None, None, None) + tuple(grads)
+
+
+def _fill_weights(params, module):
+    """params in _train_params() order -> gpp_planner_weights (running stats from the module's buffers)."""
+    w = _lib.PlannerWeights()
+    for l, ci in enumerate(_CONV_IDX):
+        bnm = module.ConvLayers[ci + 1]
+        w.conv_w[l] = params[l].data_ptr()
+        w.conv_b[l] = params[5 + l].data_ptr()
+        w.bn_w[l] = params[10 + l].data_ptr()
+        w.bn_b[l] = params[15 + l].data_ptr()
+        w.bn_mean[l] = bnm.running_mean.data_ptr()
+        w.bn_var[l] = bnm.running_var.data_ptr()
+    w.compress_w, w.compress_b = params[20].data_ptr(), params[21].data_ptr()
+    w.gf_w, w.gf_b = params[22].data_ptr(), params[23].data_ptr()
+    w.action_w, w.action_b = params[24].data_ptr(), params[25].data_ptr()
+    return w
 
 
 class _NativePlanner:
@@ -142,11 +224,20 @@ class DecentralPlannerNet(nn.Module):
         if not S.is_cuda:
             S = S.to(inputTensor.device)
         self.GFL[0].addGSO(S)
-        if not self.training and not torch.is_grad_enabled():
+        if self.training:
+            logits = _PlannerTrainFn.apply(self, inputTensor, S, *self._train_params())    # [N,B,5]
+        elif not torch.is_grad_enabled():
             logits = self._forward_fused(inputTensor, S)           # [N,B,5]
         else:
-            logits = self._forward_autograd(inputTensor, S)        # [N,B,5]
+            logits = self._forward_autograd(inputTensor, S)        # eval-mode BN under autograd (rare)
         return list(logits.unbind(0))
+
+    def _train_params(self):
+        convs = [self.ConvLayers[ci] for ci in _CONV_IDX]
+        bns = [self.ConvLayers[ci + 1] for ci in _CONV_IDX]
+        lin, gf, act = self.compressMLP[0], self.GFL[0], self.actionsMLP[0]
+        return ([c.weight for c in convs] + [c.bias for c in convs] + [b.weight for b in bns] + [b.bias for b in bns]
+                + [lin.weight, lin.bias, gf.weight, gf.bias, act.weight, act.bias])
 
     # ------------------------------------------------------- fused inference
     def _weights_key(self):

@@ -144,6 +144,45 @@ int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_
 int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,
                              int s_is_f64, float* logits_host, int B, int N);
 
+/* ------------------------------------------------------------------------------------
+ * Whole-planner TRAINING forward / backward (replaces DecentralPlannerNet.forward in train mode,
+ * decentralplanner.py:278-318, and the autograd pass behind loss.backward(),
+ * agents/decentralplannerlocal.py:297-314).  All pointers are device pointers.
+ *
+ * BatchNorm follows the reference's per-agent semantics: the reference calls ConvLayers once per agent, so
+ * batch statistics are over (B,H,W) of one agent's slice and the running statistics receive N sequential
+ * momentum updates per forward, in agent order (bn == NULL or NULL members: no running-stat update).
+ *   logits   out [N,B,5]                         dlogits  in [N,B,5]  (gradient of the loss)
+ *   workspace: gpp_planner_train_workspace_bytes(B,N,K) bytes; written by the forward (saved activations),
+ *              read and scribbled on by the backward of the SAME step.
+ *   grads: every member is overwritten (not accumulated) with the gradient of the matching parameter.
+ * ---------------------------------------------------------------------------------- */
+typedef struct gpp_planner_bn_state {
+    float* running_mean[5];
+    float* running_var[5];
+} gpp_planner_bn_state;
+
+typedef struct gpp_planner_grads {
+    float* conv_w[5];
+    float* conv_b[5];
+    float* bn_w[5];
+    float* bn_b[5];
+    float* compress_w;
+    float* compress_b;
+    float* gf_w;      /* [128,1,K,128] */
+    float* gf_b;      /* [128] */
+    float* action_w;
+    float* action_b;
+} gpp_planner_grads;
+
+size_t gpp_planner_train_workspace_bytes(int B, int N, int K);
+int gpp_planner_train_forward(const gpp_planner_weights* w, const gpp_planner_bn_state* bn, float momentum,
+                              const float* x, const void* S, int s_is_f64, float* logits, void* workspace,
+                              int B, int N, int K, void* stream);
+int gpp_planner_train_backward(const gpp_planner_weights* w, const float* x, const void* S, int s_is_f64,
+                               const float* dlogits, void* workspace, const gpp_planner_grads* g,
+                               int B, int N, int K, void* stream);
+
 /* Asynchronous variant for pipelined rollouts over independent episode batches: enqueues the same
  * zero-copy forward on the planner's stream and returns at once with a completion ticket; the host
  * buffers MUST be pinned and must stay untouched until gpp_planner_wait(ticket) returns.  Calls are

@@ -121,7 +121,7 @@ def graph_filter_f64(weight, bias, S, x) -> np.ndarray:
 # Whole planner forward
 # ----------------------------------------------------------------------------
 def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool,
-                   bn_state: Optional[Dict[str, torch.Tensor]]) -> torch.Tensor:
+                   bn_state: Optional[Dict[str, torch.Tensor]], stats: Optional[dict] = None) -> torch.Tensor:
     """ConvLayers applied to ONE agent's [B,3,11,11] slice (decentralplanner.py:286):
     5 x (Conv3x3 s1 p1 + BatchNorm2d + ReLU), MaxPool2d(2) after conv 0, 2, 4."""
     h = xi
@@ -138,6 +138,13 @@ def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool
         else:
             h = Fn.batch_norm(h, sd[p + "running_mean"], sd[p + "running_var"],
                               sd[p + "weight"], sd[p + "bias"], False, BN_MOMENTUM, BN_EPS)
+        if stats is not None:
+            # distance of the closest pre-activation to the ReLU kink, relative to the layer's scale: two correct
+            # fp32 implementations may legitimately switch such an element on/off (tests use it to pick inputs)
+            with torch.no_grad():
+                m = float(h.abs().min() / h.abs().max().clamp_min(1e-30))
+            stats.setdefault("relu_margin", [1.0] * 5)
+            stats["relu_margin"][l] = min(stats["relu_margin"][l], m)
         h = Fn.relu(h)
         if l % 2 == 0:
             h = Fn.max_pool2d(h, kernel_size=2)
@@ -146,7 +153,8 @@ def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool
 
 def planner_forward(sd: Dict[str, torch.Tensor], S: torch.Tensor, x: torch.Tensor,
                     training: bool = False,
-                    bn_state: Optional[Dict[str, torch.Tensor]] = None) -> List[torch.Tensor]:
+                    bn_state: Optional[Dict[str, torch.Tensor]] = None,
+                    stats: Optional[dict] = None) -> List[torch.Tensor]:
     """Restates DecentralPlannerNet.addGSO + forward (decentralplanner.py:266-318).
 
     sd: state_dict-keyed tensors; S [B,N,N]; x [B,N,3,11,11] f32.
@@ -159,7 +167,7 @@ def planner_forward(sd: Dict[str, torch.Tensor], S: torch.Tensor, x: torch.Tenso
     B, N = x.shape[0], x.shape[1]
     feat = torch.zeros(B, NUM_FEATURES, N)                               # :283
     for i in range(N):                                                   # :284
-        fm = _cnn_one_agent(sd, x[:, i], training, bn_state)             # :285-286
+        fm = _cnn_one_agent(sd, x[:, i], training, bn_state, stats)      # :285-286
         flat = fm.reshape(fm.shape[0], -1)                               # :287
         comp = Fn.relu(Fn.linear(flat, sd["compressMLP.0.weight"], sd["compressMLP.0.bias"]))  # :289
         feat[:, :, i] = comp                                             # :290
