@@ -31,7 +31,7 @@ constexpr int NUM_ACT = 5;
 // nks > 1 splits the j range; split ks writes its partial sums to out + ks*part_stride.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, int IS, int n_in,
-                                              const float* __restrict__ wm, int n_out,
+                                              const float* __restrict__ wm, int ldw, int n_out,
                                               float* __restrict__ out_s, int OS, int part_stride,
                                               int RP, int nks) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -43,21 +43,21 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, in
         const int rt = (item / n_cg) % n_rt;
         const int ks = item / (n_cg * n_rt);
         const int c = (cg << 5) + lane;
-        const float* wp = wm + (size_t)(ks * len) * n_out + c;
+        const float* wp = wm + (size_t)(ks * len) * ldw + c;
         const float* zr = in_s + (rt << 4) * IS + ks * len;
         float acc[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) acc[r] = 0.f;
         float wn[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wp + (size_t)j * n_out);
+        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wp + (size_t)j * ldw);
         for (int kg = 0; kg < len; kg += 8) {
             float wc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) wc[j] = wn[j];
             if (kg + 8 < len) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wn[j] = __ldg(wp + (size_t)(kg + 8 + j) * n_out);
+                for (int j = 0; j < 8; ++j) wn[j] = __ldg(wp + (size_t)(kg + 8 + j) * ldw);
             }
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
@@ -102,26 +102,31 @@ struct GfFwdArgs {
     const float* wa;      // [5][128] action weights, null: no fused action MLP
     const float* ba;      // [5]
     float* logits;        // [N][B][5]
-    int B, N, K, TS, num_tiles;
+    float* lpart;         // [csplit][B*N][5] partial logits (column-split launches only)
+    unsigned int* tickets;  // [num_tiles] arrival counters of the column halves (zero before and after a launch)
+    int B, N, K, TS, num_tiles, csplit;
     int s_is_f64, x_layout, y_layout, relu, bulk_x, bulk_s;
 };
 
 // smem carve-up shared by host (size) and device (pointers)
 struct GfFwdSmem {
-    int RP, ZS, nks, s_floats;
-    __host__ __device__ GfFwdSmem(int N, int K, int TS) {
+    int RP, ZS, nks, PS, s_floats;
+    __host__ __device__ GfFwdSmem(int N, int K, int TS, int csplit) {
         RP = ((TS * N + 15) / 16) * 16;
         ZS = K * GF_C + 4;
-        // split the K*G reduction so that the 4 column groups x row tiles x splits fill 16 warps
+        // split the K*G reduction so that the (4 / csplit) column groups x row tiles x splits fill 16 warps
         const int n_rt = RP / 16;
         nks = (n_rt >= 4 && (n_rt & 3) == 0) ? 1 : ((n_rt & 1) ? 4 : 2);
+        nks *= csplit;
+        if (nks > 8) nks = 8;
+        PS = GF_C / csplit + 4;
         s_floats = ((TS * N * N + 3) / 4) * 4;
     }
     __host__ __device__ size_t z_off() const { return 16; }
     __host__ __device__ size_t s_off() const { return z_off() + sizeof(float) * RP * ZS; }
     __host__ __device__ size_t part_off() const { return s_off() + sizeof(float) * s_floats; }
     __host__ __device__ size_t misc_off() const {
-        return part_off() + sizeof(float) * nks * RP * GF_PS;
+        return part_off() + sizeof(float) * nks * RP * PS;
     }
     __host__ __device__ size_t total() const {
         return misc_off() + sizeof(float) * (GF_C + NUM_ACT * GF_C + 8);
@@ -133,8 +138,9 @@ constexpr int GF_FWD_WARPS = GF_FWD_THREADS / 32;
 
 __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const GfFwdSmem L(a.N, a.K, a.TS);
+    const GfFwdSmem L(a.N, a.K, a.TS, a.csplit);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ unsigned int s_last;
     float* z = reinterpret_cast<float*>(smem_raw + L.z_off());
     float* Ss = reinterpret_cast<float*>(smem_raw + L.s_off());
     float* part = reinterpret_cast<float*>(smem_raw + L.part_off());
@@ -156,7 +162,13 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
     __syncthreads();
     uint32_t phase = 0;
 
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    // Column split (small batches): csplit CTAs share a tile, each contracts 128 / csplit output columns (half the
+    // tap stream, half the dependent chain); the partial action logits meet in global memory and the CTA that
+    // arrives last (ticket counter) adds them in a fixed order.
+    const int ncols = GF_C / a.csplit;
+    for (int vt = blockIdx.x; vt < a.num_tiles * a.csplit; vt += gridDim.x) {
+        const int tile = vt / a.csplit, half = vt - tile * a.csplit;
+        const int col0 = half * ncols;
         const int s0 = tile * a.TS;
         const int ns = min(a.TS, a.B - s0);
         const int R = ns * N;
@@ -233,39 +245,42 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
 
         // ---- 3. tap contraction ---------------------------------------------------------
         const int nks = L.nks;  // fixed per launch: the partial buffers are sized for it
-        tile_contract(z, ZS, K * GF_C, a.wt, GF_C, part, GF_PS, L.RP * GF_PS, RP, nks);
+        tile_contract(z, ZS, K * GF_C, a.wt + col0, GF_C, ncols, part, L.PS, L.RP * L.PS, RP, nks);
         __syncthreads();
 
         // ---- 4. epilogue: bias, ReLU, y store, fused action MLP -------------------------
-        for (int i = threadIdx.x; i < R * GF_C; i += GF_FWD_THREADS) {
-            const int r = i >> 7, f = i & 127;
-            float v = part[r * GF_PS + f];
-            for (int ks = 1; ks < nks; ++ks) v += part[ks * L.RP * GF_PS + r * GF_PS + f];
-            v += bias_s[f];
+        for (int i = threadIdx.x; i < R * ncols; i += GF_FWD_THREADS) {
+            const int r = i / ncols, f = i - r * ncols;
+            float v = part[r * L.PS + f];
+            for (int ks = 1; ks < nks; ++ks) v += part[ks * L.RP * L.PS + r * L.PS + f];
+            v += bias_s[col0 + f];
             if (a.relu) v = fmaxf(v, 0.f);
-            part[r * GF_PS + f] = v;
-            if (a.y && a.y_layout == GPP_NODE_MAJOR) a.y[(row0 + r) * GF_C + f] = v;
+            part[r * L.PS + f] = v;
+            if (a.y && a.y_layout == GPP_NODE_MAJOR) a.y[(row0 + r) * GF_C + col0 + f] = v;
         }
         __syncthreads();
         if (a.y && a.y_layout == GPP_FEATURE_MAJOR) {
-            float* yp = a.y + (size_t)s0 * GF_C * N;
-            const int per = GF_C * N;
+            const int per = ncols * N;
             for (int i = threadIdx.x; i < ns * per; i += GF_FWD_THREADS) {
                 const int bl = i / per, rem = i - bl * per;
                 const int f = rem / N, n = rem - f * N;
-                yp[i] = part[(bl * N + n) * GF_PS + f];
+                a.y[((size_t)(s0 + bl) * GF_C + col0 + f) * N + n] = part[(bl * N + n) * L.PS + f];
             }
         }
         if (a.wa) {
             // logits[n][b][:] = wa . y[b,n,:] + ba   (decentralplanner.py:309-315); one warp
             // per node row, 4 features per lane, butterfly reduction across the warp
             for (int r = warp; r < R; r += GF_FWD_WARPS) {
-                const float4 v = ld_smem4(part + r * GF_PS + lane * 4);
                 float s[NUM_ACT];
 #pragma unroll
-                for (int c = 0; c < NUM_ACT; ++c) {
-                    const float4 w = ld_smem4(wa_s + c * GF_C + lane * 4);
-                    s[c] = v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+                for (int c = 0; c < NUM_ACT; ++c) s[c] = 0.f;
+                if (lane * 4 < ncols) {
+                    const float4 v = ld_smem4(part + r * L.PS + lane * 4);
+#pragma unroll
+                    for (int c = 0; c < NUM_ACT; ++c) {
+                        const float4 w = ld_smem4(wa_s + c * GF_C + col0 + lane * 4);
+                        s[c] = v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w;
+                    }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -277,7 +292,31 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
                     float o = s[0];
 #pragma unroll
                     for (int c = 1; c < NUM_ACT; ++c) o = (lane == c) ? s[c] : o;
-                    a.logits[((size_t)n * a.B + (s0 + bl)) * NUM_ACT + lane] = o + ba_s[lane];
+                    if (a.csplit == 1)
+                        a.logits[((size_t)n * a.B + (s0 + bl)) * NUM_ACT + lane] = o + ba_s[lane];
+                    else
+                        a.lpart[((size_t)half * a.B * N + row0 + r) * NUM_ACT + lane] = o;
+                }
+            }
+            if (a.csplit > 1) {
+                __threadfence();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const unsigned int t = atomicAdd(&a.tickets[tile], 1u);
+                    s_last = (t == (unsigned int)a.csplit - 1u) ? 1u : 0u;
+                    if (s_last) a.tickets[tile] = 0u;          // ready for the next launch
+                }
+                __syncthreads();
+                if (s_last) {
+                    __threadfence();
+                    for (int i = threadIdx.x; i < R * NUM_ACT; i += GF_FWD_THREADS) {
+                        const int r = i / NUM_ACT, c = i - r * NUM_ACT;
+                        float o = ba_s[c];
+                        for (int hh = 0; hh < a.csplit; ++hh)
+                            o += __ldcg(a.lpart + ((size_t)hh * a.B * N + row0 + r) * NUM_ACT + c);
+                        const int bl = r / N, n = r - bl * N;
+                        a.logits[((size_t)n * a.B + (s0 + bl)) * NUM_ACT + c] = o;
+                    }
                 }
             }
         }
@@ -466,7 +505,7 @@ __global__ void __launch_bounds__(GF_THREADS) gf_bwd_data_kernel(const GfBwdData
         }
         if (a.dx) {
             // dZ (all taps) = dY . w   -> overwrites z
-            tile_contract(dys, GF_PS, GF_C, a.w, K * GF_C, z, ZS, 0, RP, 1);
+            tile_contract(dys, GF_PS, GF_C, a.w, K * GF_C, K * GF_C, z, ZS, 0, RP, 1);
             __syncthreads();
             // Horner: u = dZ_{K-1}; u = dZ_k + S u  (in place in slot k), k = K-2 .. 0
             for (int k = K - 2; k >= 0; --k) {
@@ -689,10 +728,12 @@ int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t
     return GPP_OK;
 }
 
+// `lpart` ([2][B*N][5] floats) and `tickets` (>= ceil(B / TS) zeroed counters) are the caller's scratch for the
+// column-split launch of small batches; without them (or without the fused action MLP) no scratch is needed.
 int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const float* wt,
                            const float* bias, float* y, const float* wa, const float* ba,
                            float* logits, int B, int N, int K, int x_layout, int y_layout,
-                           int relu, int allow_bulk, cudaStream_t st) {
+                           int relu, int allow_bulk, float* lpart, unsigned int* tickets, cudaStream_t st) {
     GfFwdArgs a;
     a.x = x; a.S = S; a.wt = wt; a.bias = bias; a.y = y; a.wa = wa; a.ba = ba; a.logits = logits;
     a.B = B; a.N = N; a.K = K;
@@ -701,7 +742,13 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
     a.s_is_f64 = s_is_f64; a.x_layout = x_layout; a.y_layout = y_layout; a.relu = relu;
     a.bulk_x = (allow_bulk && x_layout == GPP_NODE_MAJOR && aligned16(x)) ? 1 : 0;
     a.bulk_s = (allow_bulk && !s_is_f64 && aligned16(S) && ((N * N) % 4 == 0)) ? 1 : 0;
-    const GfFwdSmem L(N, K, a.TS);
+    // fewer tiles than SMs: let two CTAs share every tile (column halves)
+    a.csplit = (2 * a.num_tiles <= sm_count()) ? 2 : 1;
+    if (wa && !(lpart && tickets)) a.csplit = 1;
+    a.lpart = lpart;
+    a.tickets = tickets;
+    if (a.csplit > 1 && GfFwdSmem(N, K, a.TS, a.csplit).total() > 160 * 1024) a.csplit = 1;
+    const GfFwdSmem L(N, K, a.TS, a.csplit);
     const size_t smem = L.total();
     static size_t configured = 0;
     if (smem > configured) {
@@ -712,7 +759,8 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
     int per_sm = (int)(220 * 1024 / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
-    int grid = a.num_tiles < sm_count() * per_sm ? a.num_tiles : sm_count() * per_sm;
+    const int vtiles = a.num_tiles * a.csplit;
+    int grid = vtiles < sm_count() * per_sm ? vtiles : sm_count() * per_sm;
     gf_fwd_kernel<<<grid, GF_FWD_THREADS, smem, st>>>(a);
     GPP_LAUNCH_CHECK();
     return GPP_OK;
@@ -773,7 +821,7 @@ extern "C" int gpp_graph_filter_forward(const float* x, const void* S, int s_is_
         int rc = launch_transpose_taps(w, wt, F, K * G, st);
         if (rc) return rc;
         return launch_gf_forward_fast(x, S, s_is_f64, wt, bias, y, nullptr, nullptr, nullptr, B, N, K,
-                                      x_layout, y_layout, fuse_relu, 1, st);
+                                      x_layout, y_layout, fuse_relu, 1, nullptr, nullptr, st);
     }
     const size_t smem = generic_fwd_smem(N, G, K);
     GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED,

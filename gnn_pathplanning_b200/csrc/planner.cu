@@ -42,7 +42,7 @@ int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t
 int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const float* wt,
                            const float* bias, float* y, const float* wa, const float* ba,
                            float* logits, int B, int N, int K, int x_layout, int y_layout,
-                           int relu, int allow_bulk, cudaStream_t st);
+                           int relu, int allow_bulk, float* lpart, unsigned int* tickets, cudaStream_t st);
 // tensor-core path (graph_filter_tc.cu)
 size_t gf_tc_image_floats(int K);
 int gf_tc_tile_samples(int N, int K);
@@ -99,6 +99,8 @@ struct gpp_planner {
     size_t raw_floats;
     float* feat;         // [rows][128] workspace
     size_t feat_rows;
+    float* gf_lpart;     // [2][rows][5] partial logits + [rows] tile tickets of the column-split filter launch
+    size_t gf_lpart_rows;
     // host-buffer path
     cudaStream_t stream;
     float* d_x;
@@ -182,6 +184,7 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->arena);
     cudaFree(p->raw);
     cudaFree(p->feat);
+    cudaFree(p->gf_lpart);
     cudaFree(p->d_x);
     cudaFree(p->d_S);
     cudaFree(p->d_logits);
@@ -333,6 +336,19 @@ static int ensure_feat(gpp_planner* p, size_t rows) {
     return GPP_OK;
 }
 
+static int ensure_gf_scratch(gpp_planner* p, size_t rows) {
+    if (p->gf_lpart_rows >= rows) return GPP_OK;
+    GPP_CUDA_OK(cudaDeviceSynchronize());
+    cudaFree(p->gf_lpart);
+    p->gf_lpart = nullptr;
+    p->gf_lpart_rows = 0;
+    const size_t floats = (size_t)(2 * 5 + 1) * rows;
+    GPP_CUDA_OK(cudaMalloc(&p->gf_lpart, sizeof(float) * floats));
+    GPP_CUDA_OK(cudaMemset(p->gf_lpart, 0, sizeof(float) * floats));  // tickets start (and are left) at zero
+    p->gf_lpart_rows = rows;
+    return GPP_OK;
+}
+
 // x / S / logits may be device memory or pinned host memory mapped into the device address space
 // (zero-copy); `allow_bulk` = 0 keeps the filter kernel off the bulk-copy engine for host-mapped S.
 static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, int s_is_f64,
@@ -376,10 +392,14 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     if (use_tc)
         rc = launch_gf_forward_tc(feat, S, s_is_f64, A + p->off_gfimg, A + p->off_gfb, nullptr, A + p->off_wa,
                                   A + p->off_ba, logits, B, N, p->K, 1, allow_bulk, st);
-    else
+    else {
+        rc = ensure_gf_scratch(p, rows);
+        if (rc) return rc;
         rc = launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
                                     A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
-                                    GPP_NODE_MAJOR, 1, allow_bulk, st);
+                                    GPP_NODE_MAJOR, 1, allow_bulk, p->gf_lpart,
+                                    reinterpret_cast<unsigned int*>(p->gf_lpart + 10 * p->gf_lpart_rows), st);
+    }
     if (rc) return rc;
     if (prof) GPP_CUDA_OK(cudaEventRecord(e2, st));
     return GPP_OK;

@@ -94,6 +94,25 @@ def test_eval_vs_oracle(N, K, B, map_w):
     assert np.array_equal(got.argmax(-1)[clear], ref.argmax(-1)[clear])
 
 
+def test_repeated_calls_with_changing_batch_sizes():
+    """One handle, many launches: small batches use the column-split filter launch whose tile tickets and
+    partial-logit scratch are reused across calls and regrown when the batch grows."""
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    N, K, map_w = 10, 3, 20
+    sd = po.init_state_dict(K, seed=5)
+    po.randomize_bn_stats(sd, seed=6)
+    m = _model(sd, N, K).eval()
+    for rep, B in enumerate([7, 64, 7, 1, 200, 64, 1500, 64, 64]):
+        x, S = synthetic.make_batch(B, N, map_w, seed=100 + rep)
+        xt, St = torch.from_numpy(x), torch.from_numpy(S)
+        with torch.no_grad():
+            ref = torch.stack(po.planner_forward(sd, St, xt)).numpy()
+            m.addGSO(St.cuda())
+            got = torch.stack(m(xt.cuda())).cpu().numpy()
+        assert rel_err(got, ref) <= TOL, (rep, B)
+
+
 def test_state_dict_roundtrip_and_weight_refresh(golden):
     from oracle import planner_oracle as po
     g = golden("planner_K3.npz")
