@@ -104,6 +104,7 @@ struct GfFwdArgs {
     float* logits;        // [N][B][5]
     float* lpart;         // [csplit][B*N][5] partial logits (column-split launches only)
     unsigned int* tickets;  // [num_tiles] arrival counters of the column halves (zero before and after a launch)
+    unsigned long long* timing;  // optional [8] per-phase cycle totals of block 0 (debug), null in production
     int B, N, K, TS, num_tiles, csplit;
     int s_is_f64, x_layout, y_layout, relu, bulk_x, bulk_s;
 };
@@ -149,6 +150,14 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
     float* ba_s = wa_s + NUM_ACT * GF_C;
     const int N = a.N, K = a.K, ZS = L.ZS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool timed = a.timing && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tprev = timed ? clock64() : 0;
+#define GF_MARK(i)                                                          \
+    if (timed) {                                                            \
+        const long long tn = clock64();                                     \
+        atomicAdd(&a.timing[i], (unsigned long long)(tn - tprev));          \
+        tprev = tn;                                                         \
+    }
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -160,6 +169,7 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
         if (threadIdx.x < NUM_ACT) ba_s[threadIdx.x] = a.ba[threadIdx.x];
     }
     __syncthreads();
+    GF_MARK(0)
     uint32_t phase = 0;
 
     // Column split (small batches): csplit CTAs share a tile, each contracts 128 / csplit output columns (half the
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
             phase ^= 1;
         }
         __syncthreads();
+        GF_MARK(1)
 
         // ---- 2. propagate: z_k[n,:] = sum_m S[m,n] z_{k-1}[m,:]  (x.S of graphML.py:2350) ---
         for (int k = 1; k < K; ++k) {
@@ -243,10 +254,12 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
             __syncthreads();
         }
 
+        GF_MARK(2)
         // ---- 3. tap contraction ---------------------------------------------------------
         const int nks = L.nks;  // fixed per launch: the partial buffers are sized for it
         tile_contract(z, ZS, K * GF_C, a.wt + col0, GF_C, ncols, part, L.PS, L.RP * L.PS, RP, nks);
         __syncthreads();
+        GF_MARK(3)
 
         // ---- 4. epilogue: bias, ReLU, y store, fused action MLP -------------------------
         for (int i = threadIdx.x; i < R * ncols; i += GF_FWD_THREADS) {
@@ -267,6 +280,7 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
                 a.y[((size_t)(s0 + bl) * GF_C + col0 + f) * N + n] = part[(bl * N + n) * L.PS + f];
             }
         }
+        GF_MARK(4)
         if (a.wa) {
             // logits[n][b][:] = wa . y[b,n,:] + ba   (decentralplanner.py:309-315); one warp
             // per node row, 4 features per lane, butterfly reduction across the warp
@@ -321,7 +335,9 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
             }
         }
         __syncthreads();  // part / z / Ss are reused by the next tile
+        GF_MARK(5)
     }
+#undef GF_MARK
 }
 
 // ---------------------------------------------------------------------------------------
@@ -728,6 +744,8 @@ int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t
     return GPP_OK;
 }
 
+static unsigned long long* g_gf_timing = nullptr;  // GPP_GF_TIMING debug counters
+
 // `lpart` ([2][B*N][5] floats) and `tickets` (>= ceil(B / TS) zeroed counters) are the caller's scratch for the
 // column-split launch of small batches; without them (or without the fused action MLP) no scratch is needed.
 int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const float* wt,
@@ -747,6 +765,14 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
     if (wa && !(lpart && tickets)) a.csplit = 1;
     a.lpart = lpart;
     a.tickets = tickets;
+    a.timing = nullptr;
+    if (getenv("GPP_GF_TIMING")) {
+        if (!g_gf_timing) {
+            GPP_CUDA_OK(cudaMalloc(&g_gf_timing, 64));
+            GPP_CUDA_OK(cudaMemset(g_gf_timing, 0, 64));
+        }
+        a.timing = g_gf_timing;
+    }
     if (a.csplit > 1 && GfFwdSmem(N, K, a.TS, a.csplit).total() > 160 * 1024) a.csplit = 1;
     const GfFwdSmem L(N, K, a.TS, a.csplit);
     const size_t smem = L.total();
@@ -934,5 +960,15 @@ extern "C" int gpp_graph_filter_backward(const float* dy, const float* y, const 
         gf_bwd_generic_weight_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
         GPP_LAUNCH_CHECK();
     }
+    return GPP_OK;
+}
+
+// debug: per-phase cycle totals of block 0 of gf_fwd_kernel since the last call (only filled when GPP_GF_TIMING is
+// set): prologue, x/S staging, propagate, tap contraction, epilogue, action MLP + ticket merge.
+extern "C" int gpp_debug_gf_timing(unsigned long long* out6) {
+    if (!gpp::g_gf_timing) return GPP_ERR_INVALID;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out6, gpp::g_gf_timing, 48, cudaMemcpyDeviceToHost);
+    cudaMemset(gpp::g_gf_timing, 0, 64);
     return GPP_OK;
 }

@@ -67,6 +67,7 @@ size_t feature_tc_image_floats(int L);
 int launch_prep_feature_tc(const float* w, float* img, int L, cudaStream_t st);
 int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStream_t st);
 int debug_feature_tc_timing(unsigned long long* out20);
+int debug_feature_timing(unsigned long long* out7);
 
 // scale = gamma / sqrt(var + eps);  shift = (conv_bias - mean) * scale + beta
 __global__ void fold_bn_kernel(const float* conv_b, const float* g, const float* b, const float* mean,
@@ -212,6 +213,7 @@ extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
 
 // debug: per-layer {staging loop, wait for MMAs, epilogue} cycle totals of feature_tc_kernel + tiles at [18]
 extern "C" int gpp_debug_feature_tc_timing(unsigned long long* out20) { return debug_feature_tc_timing(out20); }
+extern "C" int gpp_debug_feature_timing(unsigned long long* out7) { return debug_feature_timing(out7); }
 
 extern "C" int gpp_planner_set_feature_mode(gpp_planner* p, int mode) {
     GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_feature_mode: mode must be 0, 1 or 2");
@@ -363,7 +365,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     }
     const float* A = p->arena;
     FeArgs fa;
-    fa.x = x; fa.feat = feat; fa.total_agents = (int)rows; fa.apt = 0; fa.num_tiles = 0;
+    fa.x = x; fa.feat = feat; fa.total_agents = (int)rows; fa.apt = 0; fa.num_tiles = 0; fa.timing = nullptr;
     fa.w0t = A + p->off_w[0]; fa.w1t = A + p->off_w[1]; fa.w2t = A + p->off_w[2];
     fa.w3t = A + p->off_w[3]; fa.w4t = A + p->off_w[4]; fa.w5t = A + p->off_w[5];
     for (int l = 0; l < 5; ++l) { fa.sc[l] = A + p->off_sc[l]; fa.sh[l] = A + p->off_sh[l]; }

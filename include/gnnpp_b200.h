@@ -208,9 +208,15 @@ int gpp_debug_umma_selftest(const float* A, const float* B, float* D, void* stre
 /* Debug: per-phase cycle totals of the tcgen05 filter kernel (filled only when the environment variable
  * GPP_TC_TIMING is set): staging loop, wait for the last MMA, TMEM read-out, propagation, stores, tiles. */
 int gpp_debug_tc_timing(unsigned long long* out6);
+/* Same for block 0 of the CUDA-core filter kernel (environment variable GPP_GF_TIMING): prologue, x/S staging,
+ * propagation, tap contraction, epilogue, action MLP + column-half merge. */
+int gpp_debug_gf_timing(unsigned long long* out6);
 /* Same for the tcgen05 feature extractor: [3*L + {0,1,2}] = layer L staging loop / wait for MMAs / epilogue,
  * [18] = agent tiles (thread 0 of every CTA). */
 int gpp_debug_feature_tc_timing(unsigned long long* out20);
+/* Block 0 of the CUDA-core feature extractor (environment variable GPP_FE_TIMING): input staging, conv0, conv1,
+ * conv2, conv3, conv4, compress MLP + store. */
+int gpp_debug_feature_timing(unsigned long long* out7);
 
 /* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
  * CUDA events before / between / after its two kernels on the launching stream (at most 8192
