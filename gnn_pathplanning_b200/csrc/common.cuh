@@ -39,6 +39,23 @@ extern thread_local unsigned long long g_launches;
 
 int sm_count();
 
+// Launch with (pdl != 0) or without the programmatic-stream-serialization attribute.
+template <typename Kernel, typename Args>
+inline cudaError_t launch_maybe_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t st, int pdl,
+                                    const Args& args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 // ---- device-side PTX helpers (Blackwell: mbarrier + 1-D bulk async copy = UBLKCP) -----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -126,6 +143,13 @@ __device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* s
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- programmatic dependent launch: the next kernel of the stream may start its prologue early; its reads of
+//      anything the previous kernels wrote come after griddep_wait() ------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 __device__ __forceinline__ float4 ld_smem4(const float* p) {

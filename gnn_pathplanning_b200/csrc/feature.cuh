@@ -19,6 +19,7 @@ struct FeArgs {
     const float* sc[5];   // eval-mode BatchNorm folded to a per-channel scale ...
     const float* sh[5];   // ... and shift (conv bias included)
     const float* b5;      // compress bias
+    int pdl;              // launched with programmatic stream serialization: wait before reading x
     unsigned long long* timing;  // optional [8] per-phase cycle totals of block 0 (debug, GPP_FE_TIMING); null otherwise
 };
 

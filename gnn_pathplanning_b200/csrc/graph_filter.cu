@@ -30,10 +30,12 @@ constexpr int NUM_ACT = 5;
 // the 16 rows of a register tile read `in` through warp-broadcast LDS.128.
 // nks > 1 splits the j range; split ks writes its partial sums to out + ks*part_stride.
 // ---------------------------------------------------------------------------------------
+// WS: the weights are in shared memory, slice ks of the reduction range guarded by mbarrier wbar[ks]
+template <bool WS>
 __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, int IS, int n_in,
                                               const float* __restrict__ wm, int ldw, int n_out,
                                               float* __restrict__ out_s, int OS, int part_stride,
-                                              int RP, int nks) {
+                                              int RP, int nks, uint64_t* wbar = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int n_cg = n_out >> 5, n_rt = RP >> 4;
     const int n_items = n_cg * n_rt * nks;
@@ -49,30 +51,43 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, in
 #pragma unroll
         for (int r = 0; r < 16; ++r) acc[r] = 0.f;
         float wn[8];
+        if (WS) mbar_wait(wbar + ks, 0);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wn[j] = __ldg(wp + (size_t)j * ldw);
+        for (int j = 0; j < 8; ++j) wn[j] = WS ? wp[j * ldw] : __ldg(wp + (size_t)j * ldw);
         for (int kg = 0; kg < len; kg += 8) {
             float wc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) wc[j] = wn[j];
             if (kg + 8 < len) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) wn[j] = __ldg(wp + (size_t)(kg + 8 + j) * ldw);
+                for (int j = 0; j < 8; ++j)
+                    wn[j] = WS ? wp[(kg + 8 + j) * ldw] : __ldg(wp + (size_t)(kg + 8 + j) * ldw);
             }
+            // four rows at a time: four independent FMA chains per lane
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const float4 a = ld_smem4(zr + r * IS + kg);
-                const float4 b = ld_smem4(zr + r * IS + kg + 4);
-                float t = acc[r];
-                t = fmaf(a.x, wc[0], t);
-                t = fmaf(a.y, wc[1], t);
-                t = fmaf(a.z, wc[2], t);
-                t = fmaf(a.w, wc[3], t);
-                t = fmaf(b.x, wc[4], t);
-                t = fmaf(b.y, wc[5], t);
-                t = fmaf(b.z, wc[6], t);
-                t = fmaf(b.w, wc[7], t);
-                acc[r] = t;
+            for (int r = 0; r < 16; r += 4) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a[i] = ld_smem4(zr + (r + i) * IS + kg);
+                    b[i] = ld_smem4(zr + (r + i) * IS + kg + 4);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].x, wc[0], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].y, wc[1], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].z, wc[2], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].w, wc[3], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].x, wc[4], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].y, wc[5], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].z, wc[6], acc[r + i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].w, wc[7], acc[r + i]);
             }
         }
         float* op = out_s + ks * part_stride + (rt << 4) * OS + c;
@@ -97,6 +112,7 @@ struct GfFwdArgs {
     const float* x;
     const void* S;
     const float* wt;      // [K*128][128] k-major taps
+    const float* wsplit;  // [2][K*128][64] the same, column halves contiguous (w_smem launches)
     const float* bias;    // [128] or null
     float* y;             // null: do not write y
     const float* wa;      // [5][128] action weights, null: no fused action MLP
@@ -107,12 +123,15 @@ struct GfFwdArgs {
     unsigned long long* timing;  // optional [8] per-phase cycle totals of block 0 (debug), null in production
     int B, N, K, TS, num_tiles, csplit;
     int s_is_f64, x_layout, y_layout, relu, bulk_x, bulk_s;
+    int w_smem;           // column-split launch with one tile per CTA: this CTA's half of the taps is staged in smem
+    int pdl;              // launched with programmatic stream serialization: wait before touching x
 };
 
 // smem carve-up shared by host (size) and device (pointers)
 struct GfFwdSmem {
-    int RP, ZS, nks, PS, s_floats;
-    __host__ __device__ GfFwdSmem(int N, int K, int TS, int csplit) {
+    int RP, ZS, nks, PS, s_floats, w_floats;
+    __host__ __device__ GfFwdSmem(int N, int K, int TS, int csplit, int w_smem) {
+        w_floats = w_smem ? K * GF_C * (GF_C / 2) : 0;
         RP = ((TS * N + 15) / 16) * 16;
         ZS = K * GF_C + 4;
         // split the K*G reduction so that the (4 / csplit) column groups x row tiles x splits fill 16 warps
@@ -123,24 +142,25 @@ struct GfFwdSmem {
         PS = GF_C / csplit + 4;
         s_floats = ((TS * N * N + 3) / 4) * 4;
     }
-    __host__ __device__ size_t z_off() const { return 16; }
+    __host__ __device__ size_t z_off() const { return 96; }   // [0] staging barrier, [16..80) tap-slice barriers
     __host__ __device__ size_t s_off() const { return z_off() + sizeof(float) * RP * ZS; }
     __host__ __device__ size_t part_off() const { return s_off() + sizeof(float) * s_floats; }
     __host__ __device__ size_t misc_off() const {
         return part_off() + sizeof(float) * nks * RP * PS;
     }
-    __host__ __device__ size_t total() const {
-        return misc_off() + sizeof(float) * (GF_C + NUM_ACT * GF_C + 8);
-    }
+    __host__ __device__ size_t w_off() const { return misc_off() + sizeof(float) * (GF_C + NUM_ACT * GF_C + 8); }
+    __host__ __device__ size_t total() const { return w_off() + sizeof(float) * w_floats; }
 };
 
 constexpr int GF_FWD_THREADS = 512;
 constexpr int GF_FWD_WARPS = GF_FWD_THREADS / 32;
 
-__global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs a) {
+__global__ void __launch_bounds__(GF_FWD_THREADS, 1) gf_fwd_kernel(const GfFwdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const GfFwdSmem L(a.N, a.K, a.TS, a.csplit);
+    const GfFwdSmem L(a.N, a.K, a.TS, a.csplit, a.w_smem);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + 16);
+    float* wts = reinterpret_cast<float*>(smem_raw + L.w_off());
     __shared__ unsigned int s_last;
     float* z = reinterpret_cast<float*>(smem_raw + L.z_off());
     float* Ss = reinterpret_cast<float*>(smem_raw + L.s_off());
@@ -161,7 +181,21 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        fence_mbar_init();
+        if (a.w_smem) {
+            // the taps do not depend on the previous kernel: their copy is in flight while x / S are staged and
+            // propagated; one barrier per slice of the reduction range so that warps start as their slice lands
+            const int len = a.K * GF_C / L.nks;
+            const uint32_t bytes = (uint32_t)len * (GF_C / 2) * 4u;
+            for (int ks = 0; ks < L.nks; ++ks) mbar_init(wbar + ks, 1);
+            fence_mbar_init();
+            const float* src = a.wsplit + (size_t)(blockIdx.x % a.csplit) * a.K * GF_C * (GF_C / 2);
+            for (int ks = 0; ks < L.nks; ++ks) {
+                mbar_arrive_expect_tx(wbar + ks, bytes);
+                bulk_g2s(wts + (size_t)ks * len * (GF_C / 2), src + (size_t)ks * len * (GF_C / 2), bytes, wbar + ks);
+            }
+        } else {
+            fence_mbar_init();
+        }
     }
     for (int i = threadIdx.x; i < GF_C; i += GF_FWD_THREADS) bias_s[i] = a.bias ? a.bias[i] : 0.f;
     if (a.wa) {
@@ -169,6 +203,10 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
         if (threadIdx.x < NUM_ACT) ba_s[threadIdx.x] = a.ba[threadIdx.x];
     }
     __syncthreads();
+    if (a.pdl) {
+        griddep_wait();                 // x (the feature kernel's output) is complete and visible from here on
+        griddep_launch_dependents();
+    }
     GF_MARK(0)
     uint32_t phase = 0;
 
@@ -257,7 +295,10 @@ __global__ void __launch_bounds__(GF_FWD_THREADS) gf_fwd_kernel(const GfFwdArgs 
         GF_MARK(2)
         // ---- 3. tap contraction ---------------------------------------------------------
         const int nks = L.nks;  // fixed per launch: the partial buffers are sized for it
-        tile_contract(z, ZS, K * GF_C, a.wt + col0, GF_C, ncols, part, L.PS, L.RP * L.PS, RP, nks);
+        if (a.w_smem)
+            tile_contract<true>(z, ZS, K * GF_C, wts, GF_C / 2, ncols, part, L.PS, L.RP * L.PS, RP, nks, wbar);
+        else
+            tile_contract<false>(z, ZS, K * GF_C, a.wt + col0, GF_C, ncols, part, L.PS, L.RP * L.PS, RP, nks);
         __syncthreads();
         GF_MARK(3)
 
@@ -405,6 +446,14 @@ __global__ void transpose_taps_kernel(const float* __restrict__ w, float* __rest
     }
 }
 
+// ws[(h*KG + j)*64 + c] = wt[j*128 + h*64 + c]: the two column halves of the k-major taps, each contiguous
+__global__ void split_taps_kernel(const float* __restrict__ wt, float* __restrict__ ws, int KG) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= KG * GF_C) return;
+    const int j = i / GF_C, f = i - j * GF_C;
+    ws[((size_t)(f >> 6) * KG + j) * (GF_C / 2) + (f & 63)] = wt[i];
+}
+
 // =======================================================================================
 // Backward
 //   dZ_k[r,g] = sum_f dY[r,f] w[f,k,g]          (tile_contract against w in its own layout)
@@ -521,7 +570,7 @@ __global__ void __launch_bounds__(GF_THREADS) gf_bwd_data_kernel(const GfBwdData
         }
         if (a.dx) {
             // dZ (all taps) = dY . w   -> overwrites z
-            tile_contract(dys, GF_PS, GF_C, a.w, K * GF_C, K * GF_C, z, ZS, 0, RP, 1);
+            tile_contract<false>(dys, GF_PS, GF_C, a.w, K * GF_C, K * GF_C, z, ZS, 0, RP, 1);
             __syncthreads();
             // Horner: u = dZ_{K-1}; u = dZ_k + S u  (in place in slot k), k = K-2 .. 0
             for (int k = K - 2; k >= 0; --k) {
@@ -744,6 +793,13 @@ int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t
     return GPP_OK;
 }
 
+int launch_split_taps(const float* wt, float* ws, int KG, cudaStream_t st) {
+    const int n = KG * GF_C;
+    split_taps_kernel<<<(n + 255) / 256, 256, 0, st>>>(wt, ws, KG);
+    GPP_LAUNCH_CHECK();
+    return GPP_OK;
+}
+
 static unsigned long long* g_gf_timing = nullptr;  // GPP_GF_TIMING debug counters
 
 // `lpart` ([2][B*N][5] floats) and `tickets` (>= ceil(B / TS) zeroed counters) are the caller's scratch for the
@@ -751,8 +807,11 @@ static unsigned long long* g_gf_timing = nullptr;  // GPP_GF_TIMING debug counte
 int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const float* wt,
                            const float* bias, float* y, const float* wa, const float* ba,
                            float* logits, int B, int N, int K, int x_layout, int y_layout,
-                           int relu, int allow_bulk, float* lpart, unsigned int* tickets, cudaStream_t st) {
+                           int relu, int allow_bulk, float* lpart, unsigned int* tickets, const float* wsplit,
+                           int pdl, cudaStream_t st) {
     GfFwdArgs a;
+    a.wsplit = wsplit;
+    a.pdl = pdl;
     a.x = x; a.S = S; a.wt = wt; a.bias = bias; a.y = y; a.wa = wa; a.ba = ba; a.logits = logits;
     a.B = B; a.N = N; a.K = K;
     a.TS = pick_tile_samples(B, N);
@@ -773,8 +832,10 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
         }
         a.timing = g_gf_timing;
     }
-    if (a.csplit > 1 && GfFwdSmem(N, K, a.TS, a.csplit).total() > 160 * 1024) a.csplit = 1;
-    const GfFwdSmem L(N, K, a.TS, a.csplit);
+    if (a.csplit > 1 && GfFwdSmem(N, K, a.TS, a.csplit, 0).total() > 160 * 1024) a.csplit = 1;
+    // one tile per CTA in split launches (2 * num_tiles <= SMs): stage the CTA's half of the taps in smem if it fits
+    a.w_smem = (a.csplit == 2 && wsplit && GfFwdSmem(N, K, a.TS, 2, 1).total() <= 220 * 1024) ? 1 : 0;
+    const GfFwdSmem L(N, K, a.TS, a.csplit, a.w_smem);
     const size_t smem = L.total();
     static size_t configured = 0;
     if (smem > configured) {
@@ -782,12 +843,15 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
                                          (int)smem));
         configured = smem;
     }
-    int per_sm = (int)(220 * 1024 / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_fwd_kernel, GF_FWD_THREADS, smem) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
     const int vtiles = a.num_tiles * a.csplit;
     int grid = vtiles < sm_count() * per_sm ? vtiles : sm_count() * per_sm;
-    gf_fwd_kernel<<<grid, GF_FWD_THREADS, smem, st>>>(a);
+    GPP_CUDA_OK(launch_maybe_pdl(gf_fwd_kernel, grid, GF_FWD_THREADS, smem, st, pdl, a));
     GPP_LAUNCH_CHECK();
     return GPP_OK;
 }
@@ -847,7 +911,7 @@ extern "C" int gpp_graph_filter_forward(const float* x, const void* S, int s_is_
         int rc = launch_transpose_taps(w, wt, F, K * G, st);
         if (rc) return rc;
         return launch_gf_forward_fast(x, S, s_is_f64, wt, bias, y, nullptr, nullptr, nullptr, B, N, K,
-                                      x_layout, y_layout, fuse_relu, 1, nullptr, nullptr, st);
+                                      x_layout, y_layout, fuse_relu, 1, nullptr, nullptr, nullptr, 0, st);
     }
     const size_t smem = generic_fwd_smem(N, G, K);
     GPP_REQUIRE(smem <= 200 * 1024, GPP_ERR_UNSUPPORTED,

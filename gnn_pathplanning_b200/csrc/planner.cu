@@ -39,10 +39,12 @@ int sm_count() {
 
 // internal launchers from graph_filter.cu
 int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t st);
+int launch_split_taps(const float* wt, float* ws, int KG, cudaStream_t st);
 int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const float* wt,
                            const float* bias, float* y, const float* wa, const float* ba,
                            float* logits, int B, int N, int K, int x_layout, int y_layout,
-                           int relu, int allow_bulk, float* lpart, unsigned int* tickets, cudaStream_t st);
+                           int relu, int allow_bulk, float* lpart, unsigned int* tickets, const float* wsplit,
+                           int pdl, cudaStream_t st);
 // tensor-core path (graph_filter_tc.cu)
 size_t gf_tc_image_floats(int K);
 int gf_tc_tile_samples(int N, int K);
@@ -91,7 +93,9 @@ struct gpp_planner {
     float* arena;        // prepared weights
     size_t off_w[6];     // conv0..4 k-major, compress k-major
     size_t off_sc[5], off_sh[5];
-    size_t off_b5, off_gfw, off_gfb, off_wa, off_ba, off_gfimg, arena_floats;
+    size_t off_b5, off_gfw, off_gfws, off_gfb, off_wa, off_ba, off_gfimg, arena_floats;
+    bool pdl_ok;         // the kernels before the next forward in its stream only wrote what it reads after its
+                         // griddepcontrol.wait (false right after the weights were re-staged)
     int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
     int fe_mode;         // feature extractor: 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
     size_t off_fimg[6];  // tcgen05 filter chunk images of conv0..4 and the compress MLP
@@ -159,6 +163,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     for (int l = 0; l < 5; ++l) { p->off_sc[l] = take(kConvC[l + 1]); p->off_sh[l] = take(kConvC[l + 1]); }
     p->off_b5 = take(128);
     p->off_gfw = take((size_t)K * 128 * 128);
+    p->off_gfws = take((size_t)K * 128 * 128);       // the same taps, column halves contiguous
     p->off_gfb = take(128);
     p->off_wa = take(5 * 128);
     p->off_ba = take(64);
@@ -315,6 +320,9 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     if (rc) return rc;
     rc = launch_transpose_taps(d.gf_w, A + p->off_gfw, 128, K * 128, st);
     if (rc) return rc;
+    rc = launch_split_taps(A + p->off_gfw, A + p->off_gfws, K * 128, st);
+    p->pdl_ok = false;
+    if (rc) return rc;
     rc = launch_prep_umma_taps(d.gf_w, A + p->off_gfimg, K, st);
     if (rc) return rc;
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_b5, d.compress_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
@@ -366,6 +374,11 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     const float* A = p->arena;
     FeArgs fa;
     fa.x = x; fa.feat = feat; fa.total_agents = (int)rows; fa.apt = 0; fa.num_tiles = 0; fa.timing = nullptr;
+    // programmatic dependent launch: each kernel's prologue (barriers, filter prefetch) overlaps the tail of the
+    // kernel before it; not for the first forward after the weights changed (the prologue reads them)
+    static const bool pdl_env = getenv("GPP_NO_PDL") == nullptr;
+    const int pdl = (pdl_env && p->pdl_ok && !p->profiling) ? 1 : 0;
+    fa.pdl = pdl;
     fa.w0t = A + p->off_w[0]; fa.w1t = A + p->off_w[1]; fa.w2t = A + p->off_w[2];
     fa.w3t = A + p->off_w[3]; fa.w4t = A + p->off_w[4]; fa.w5t = A + p->off_w[5];
     for (int l = 0; l < 5; ++l) { fa.sc[l] = A + p->off_sc[l]; fa.sh[l] = A + p->off_sh[l]; }
@@ -400,16 +413,20 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         rc = launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
                                     A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
                                     GPP_NODE_MAJOR, 1, allow_bulk, p->gf_lpart,
-                                    reinterpret_cast<unsigned int*>(p->gf_lpart + 10 * p->gf_lpart_rows), st);
+                                    reinterpret_cast<unsigned int*>(p->gf_lpart + 10 * p->gf_lpart_rows),
+                                    A + p->off_gfws, pdl, st);
     }
     if (rc) return rc;
     if (prof) GPP_CUDA_OK(cudaEventRecord(e2, st));
+    p->pdl_ok = true;
     return GPP_OK;
 }
 
 extern "C" int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_f64,
                                    float* logits, float* features_out, int B, int N, void* stream) {
     GPP_REQUIRE(p && x && S && logits, GPP_ERR_INVALID, "planner_forward: null pointer");
+    GPP_REQUIRE((reinterpret_cast<uintptr_t>(features_out) & 15) == 0, GPP_ERR_INVALID,
+                "planner_forward: features_out must be 16-byte aligned");
     GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward: gpp_planner_set_weights not called");
     GPP_REQUIRE(B >= 0 && N >= 1, GPP_ERR_INVALID, "planner_forward: bad sizes B=%d N=%d", B, N);
     GPP_REQUIRE(N <= 64, GPP_ERR_UNSUPPORTED, "planner_forward: N=%d > 64 agents is outside the fused kernel's tile", N);
