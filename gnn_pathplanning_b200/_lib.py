@@ -38,7 +38,7 @@ EXPORTED = (
     "gpp_planner_forward", "gpp_planner_forward_host",
     "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward",
     "gpp_planner_forward_host_async", "gpp_planner_wait", "gpp_debug_tc_timing", "gpp_debug_gf_timing",
-    "gpp_debug_feature_tc_timing", "gpp_debug_feature_timing",
+    "gpp_debug_feature_tc_timing", "gpp_debug_feature_timing", "gpp_debug_train_kernel",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
     "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode", "gpp_debug_umma_selftest",
     "gpp_launch_count", "gpp_reset_launch_count",

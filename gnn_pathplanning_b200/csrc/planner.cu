@@ -63,6 +63,23 @@ __global__ void __launch_bounds__(256) stage_h2d_kernel(const uint4* __restrict_
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
     if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
 }
+// both inputs of a step in one launch: blocks [0, gridDim.x - 1) copy x, the last block copies S
+struct StagePair {
+    const uint4* src[2];
+    uint4* dst[2];
+    size_t n16[2];
+    int tail[2];
+};
+__global__ void __launch_bounds__(256) stage_h2d_pair_kernel(const StagePair sp) {
+    const int which = blockIdx.x == gridDim.x - 1 ? 1 : 0;
+    const int nb = which ? 1 : gridDim.x - 1, b = which ? 0 : blockIdx.x;
+    const uint4* __restrict__ src = sp.src[which];
+    uint4* __restrict__ dst = sp.dst[which];
+    const size_t n16 = sp.n16[which], stride = (size_t)nb * blockDim.x;
+    for (size_t i = (size_t)b * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+    if (b == 0 && (int)threadIdx.x < sp.tail[which])
+        reinterpret_cast<unsigned char*>(dst + n16)[threadIdx.x] = reinterpret_cast<const unsigned char*>(src + n16)[threadIdx.x];
+}
 
 // tensor-core feature extractor (feature_tc.cu)
 size_t feature_tc_image_floats(int L);
@@ -88,6 +105,8 @@ using namespace gpp;
 static const int kConvC[6] = {3, 32, 32, 64, 64, 128};
 static const int IN_PIX = 3 * 11 * 11;
 
+constexpr int kStageSlots = 3;   // device staging slots of the pipelined host-buffer path (steps in flight)
+
 struct gpp_planner {
     int K;
     float* arena;        // prepared weights
@@ -104,6 +123,9 @@ struct gpp_planner {
     size_t raw_floats;
     float* feat;         // [rows][128] workspace
     size_t feat_rows;
+    const void* alias_host[16];   // pinned host buffers seen by the async entry point and their device aliases
+    void* alias_dev[16];
+    unsigned alias_next;
     float* gf_lpart;     // [2][rows][5] partial logits + [rows] tile tickets of the column-split filter launch
     size_t gf_lpart_rows;
     // host-buffer path
@@ -118,11 +140,11 @@ struct gpp_planner {
     cudaEvent_t tickets[16];
     unsigned long long next_ticket;
     cudaStream_t copy_stream;
-    float* a_x[2];
-    size_t a_x_floats[2];
-    void* a_S[2];
-    size_t a_S_bytes[2];
-    cudaEvent_t copied[2];
+    float* a_x[kStageSlots];
+    size_t a_x_floats[kStageSlots];
+    void* a_S[kStageSlots];
+    size_t a_S_bytes[kStageSlots];
+    cudaEvent_t copied[kStageSlots];
     // per-kernel event log (roofline report)
     bool profiling;
     std::vector<cudaEvent_t>* events;   // triples: start, after feature kernel, after filter kernel
@@ -197,7 +219,7 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     if (p->stream) cudaStreamDestroy(p->stream);
     for (int i = 0; i < 16; ++i)
         if (p->tickets[i]) cudaEventDestroy(p->tickets[i]);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStageSlots; ++i) {
         cudaFree(p->a_x[i]);
         cudaFree(p->a_S[i]);
         if (p->copied[i]) cudaEventDestroy(p->copied[i]);
@@ -446,6 +468,20 @@ static void* mapped_alias(const void* host_ptr) {
     if (at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
     return nullptr;
 }
+// The per-step calls of a rollout cycle through a handful of pinned buffers: remember their device aliases
+// (a pinned allocation keeps its alias for its lifetime; a freed one that comes back is simply looked up again
+// after it falls out of the 16 most recent entries or fails the cheap pointer check below).
+static void* mapped_alias_cached(gpp_planner* p, const void* host_ptr) {
+    for (int i = 0; i < 16; ++i)
+        if (p->alias_host[i] == host_ptr && host_ptr) return p->alias_dev[i];
+    void* d = mapped_alias(host_ptr);
+    if (d) {
+        const int i = (int)(p->alias_next++ & 15);
+        p->alias_host[i] = host_ptr;
+        p->alias_dev[i] = d;
+    }
+    return d;
+}
 
 extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const void* S_host,
                                               int s_is_f64, float* logits_host, int B, int N,
@@ -453,9 +489,9 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     GPP_REQUIRE(p && x_host && S_host && logits_host && ticket, GPP_ERR_INVALID, "planner_forward_host_async: null pointer");
     GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward_host_async: gpp_planner_set_weights not called");
     GPP_REQUIRE(B >= 1 && N >= 1 && N <= 64, GPP_ERR_INVALID, "planner_forward_host_async: bad sizes B=%d N=%d", B, N);
-    void* mx = mapped_alias(x_host);
-    void* mS = mapped_alias(S_host);
-    void* ml = mapped_alias(logits_host);
+    void* mx = mapped_alias_cached(p, x_host);
+    void* mS = mapped_alias_cached(p, S_host);
+    void* ml = mapped_alias_cached(p, logits_host);
     GPP_REQUIRE(mx && mS && ml, GPP_ERR_INVALID,
                 "planner_forward_host_async: buffers must be pinned (page-locked) host memory");
     GPP_REQUIRE((reinterpret_cast<uintptr_t>(mx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(mS) & 15u) == 0,
@@ -464,10 +500,10 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     cudaEvent_t& ev = p->tickets[t % 16];
     if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     // Pipelined path: the inputs of this step are pulled over PCIe by a small staging kernel on a copy
-    // stream into one of two device slots while the kernels of the previous step run on the compute stream (a kernel that reads its
+    // stream into one of three device slots while the kernels of the previous step run on the compute stream (a kernel that reads its
     // input straight over PCIe cannot overlap that read with its own compute); the logits are still
-    // written straight into the pinned host buffer.  Slot reuse waits for the step two tickets back.
-    const int slot = (int)(t & 1);
+    // written straight into the pinned host buffer.  Slot reuse waits for the step three tickets back.
+    const int slot = (int)(t % kStageSlots);
     const size_t nx = (size_t)B * N * IN_PIX;
     const size_t sb = (size_t)B * N * N * (s_is_f64 ? 8 : 4);
     if (!p->copy_stream) GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
@@ -486,18 +522,16 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
             p->a_S_bytes[slot] = sb;
         }
     }
-    if (t >= 2) GPP_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->tickets[(t - 2) % 16], 0));
+    if (t >= (unsigned long long)kStageSlots)
+        GPP_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->tickets[(t - kStageSlots) % 16], 0));
     {
         const size_t xb = sizeof(float) * nx;
-        stage_h2d_kernel<<<8, 256, 0, p->copy_stream>>>(
-            reinterpret_cast<const uint4*>(mx), reinterpret_cast<uint4*>(p->a_x[slot]), xb / 16,
-            reinterpret_cast<const unsigned char*>(mx) + (xb / 16) * 16,
-            reinterpret_cast<unsigned char*>(p->a_x[slot]) + (xb / 16) * 16, (int)(xb % 16));
-        GPP_LAUNCH_CHECK();
-        stage_h2d_kernel<<<1, 256, 0, p->copy_stream>>>(
-            reinterpret_cast<const uint4*>(mS), reinterpret_cast<uint4*>(p->a_S[slot]), sb / 16,
-            reinterpret_cast<const unsigned char*>(mS) + (sb / 16) * 16,
-            reinterpret_cast<unsigned char*>(p->a_S[slot]) + (sb / 16) * 16, (int)(sb % 16));
+        StagePair sp;
+        sp.src[0] = reinterpret_cast<const uint4*>(mx); sp.dst[0] = reinterpret_cast<uint4*>(p->a_x[slot]);
+        sp.n16[0] = xb / 16; sp.tail[0] = (int)(xb % 16);
+        sp.src[1] = reinterpret_cast<const uint4*>(mS); sp.dst[1] = reinterpret_cast<uint4*>(p->a_S[slot]);
+        sp.n16[1] = sb / 16; sp.tail[1] = (int)(sb % 16);
+        stage_h2d_pair_kernel<<<16 + 1, 256, 0, p->copy_stream>>>(sp);
         GPP_LAUNCH_CHECK();
     }
     GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));

@@ -347,23 +347,38 @@ class DecentralPlannerNet(nn.Module):
         step's logits are in `out_host`.  All three tensors must be pinned and must not be touched in
         between.  Steps execute in issue order."""
         assert not self.training, "infer_host_async is the eval-mode rollout path"
-        assert x_host.is_pinned() and S_host.is_pinned() and out_host.is_pinned(), "pinned host tensors required"
+        # (pinned-ness and alignment are checked by the C entry point; this is the per-step hot path)
         assert x_host.dtype == torch.float32 and x_host.is_contiguous() and S_host.is_contiguous()
         assert S_host.dim() == 3 and S_host.dtype in (torch.float32, torch.float64)
         B, N = x_host.shape[0], x_host.shape[1]
         assert tuple(out_host.shape) == (N, B, 5) and out_host.dtype == torch.float32 and out_host.is_contiguous()
-        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if device is not None:
+            dev = torch.device(device)
+        else:
+            dev = self.__dict__.get("_param_device")
+            if dev is None or self.__dict__.get("_key_tensors") is None or self._key_tensors_device() != dev:
+                dev = next(self.parameters()).device
+                self.__dict__["_param_device"] = dev
         nat = self._native_for(dev)
         if getattr(nat, "fresh", False):
             torch.cuda.current_stream(dev).synchronize()
             nat.fresh = False
         t = C.c_ulonglong()
-        with torch.cuda.device(dev):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if torch.cuda.current_device() == idx:
             _lib.check(nat.lib.gpp_planner_forward_host_async(
                 nat.handle, x_host.data_ptr(), S_host.data_ptr(), int(S_host.dtype == torch.float64),
                 out_host.data_ptr(), B, N, C.byref(t)))
+        else:
+            with torch.cuda.device(idx):
+                _lib.check(nat.lib.gpp_planner_forward_host_async(
+                    nat.handle, x_host.data_ptr(), S_host.data_ptr(), int(S_host.dtype == torch.float64),
+                    out_host.data_ptr(), B, N, C.byref(t)))
         self.__dict__["_async_native"] = nat
         return int(t.value)
+
+    def _key_tensors_device(self):
+        return self.__dict__["_key_tensors"][0].device
 
     def wait(self, ticket: int) -> None:
         nat = self.__dict__["_async_native"]

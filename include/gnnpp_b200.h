@@ -217,6 +217,10 @@ int gpp_debug_feature_tc_timing(unsigned long long* out20);
 /* Block 0 of the CUDA-core feature extractor (environment variable GPP_FE_TIMING): input staging, conv0, conv1,
  * conv2, conv3, conv4, compress MLP + store. */
 int gpp_debug_feature_timing(unsigned long long* out7);
+/* Single kernels of the native training path (profiles/debug_train_ops.py): op 0 conv3x3 forward (a = input, b = filters,
+ * c = bias), op 1 conv3x3 input gradient (a = dz, b = filters), op 2 max-pool gradient (a = activation, b = pooled grad). */
+int gpp_debug_train_kernel(int op, const float* a, const float* b, const float* c, float* out, int M, int Cin, int Cout,
+                           int H, void* stream);
 
 /* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
  * CUDA events before / between / after its two kernels on the launching stream (at most 8192
