@@ -25,18 +25,30 @@ constexpr int GF_MAX_ROWS = 64;  // node rows per tile on the fast path
 constexpr int NUM_ACT = 5;
 
 // ---------------------------------------------------------------------------------------
-// out[r][c] = sum_j in[r][j] * wm[j*n_out + c]   r < RP (mult of 16), c < n_out (mult of 32)
-// Lanes own consecutive output columns (coalesced weight loads, conflict-free smem stores);
-// the 16 rows of a register tile read `in` through warp-broadcast LDS.128.
-// nks > 1 splits the j range; split ks writes its partial sums to out + ks*part_stride.
-// ---------------------------------------------------------------------------------------
+// out[r][c] = sum_j in[r][j] * wm[j*ldw + c]   r < RP (mult of 16), c < n_out (mult of 32)
+// A warp item is a 16-row x 32-column tile over one slice of the j range.  Shared memory returns 4 B per
+// lane per clock while the FMA pipes take 4 operands per lane per clock, so every float read from shared
+// memory has to feed >= 4 FMAs: each lane owns a 16 x 4 register tile (the 8 lanes of a quarter-warp cover
+// the 32 columns, weights as one 16-byte load per row of wm), the 4 quarter-warps take every 4th group of
+// 4 j's and meet through two shuffles per accumulator.  The rows of `in` are read as quarter-warp-uniform
+// LDS.128 (a 128-bit load is served one quarter-warp at a time, so 4 addresses per instruction are free).
+// nks > 1 splits the j range over items; slice ks writes its partial sums to out + ks*part_stride.
+// Needs (n_in / nks) % 16 == 0, ldw % 4 == 0 and 16-byte aligned wm / in / out rows.
 // WS: the weights are in shared memory, slice ks of the reduction range guarded by mbarrier wbar[ks]
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
 template <bool WS>
 __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, int IS, int n_in,
                                               const float* __restrict__ wm, int ldw, int n_out,
                                               float* __restrict__ out_s, int OS, int part_stride,
                                               int RP, int nks, uint64_t* wbar = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int qw = lane >> 3, l8 = lane & 7;
     const int n_cg = n_out >> 5, n_rt = RP >> 4;
     const int n_items = n_cg * n_rt * nks;
     const int len = n_in / nks;
@@ -44,55 +56,62 @@ __device__ __forceinline__ void tile_contract(const float* __restrict__ in_s, in
         const int cg = item % n_cg;
         const int rt = (item / n_cg) % n_rt;
         const int ks = item / (n_cg * n_rt);
-        const int c = (cg << 5) + lane;
-        const float* wp = wm + (size_t)(ks * len) * ldw + c;
-        const float* zr = in_s + (rt << 4) * IS + ks * len;
-        float acc[16];
+        const int c4 = (cg << 5) + l8 * 4;
+        const float* wp = wm + (size_t)(ks * len + qw * 4) * ldw + c4;
+        const float* zr = in_s + (rt << 4) * IS + ks * len + qw * 4;
+        float acc[16][4];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-        float wn[8];
+        for (int r = 0; r < 16; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
         if (WS) mbar_wait(wbar + ks, 0);
+        float4 wn[4];
+        if (!WS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) wn[j] = WS ? wp[j * ldw] : __ldg(wp + (size_t)j * ldw);
-        for (int kg = 0; kg < len; kg += 8) {
-            float wc[8];
+            for (int j = 0; j < 4; ++j) wn[j] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)j * ldw));
+        }
+        for (int kb = 0; kb < len; kb += 16) {
+            float4 w[4];
+            if (WS) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) wc[j] = wn[j];
-            if (kg + 8 < len) {
+                for (int j = 0; j < 4; ++j) w[j] = ld_smem4(wp + (kb + j) * ldw);
+            } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    wn[j] = WS ? wp[(kg + 8 + j) * ldw] : __ldg(wp + (size_t)(kg + 8 + j) * ldw);
+                for (int j = 0; j < 4; ++j) w[j] = wn[j];
+                if (kb + 16 < len) {     // next block's filter rows are in flight while this one is used
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        wn[j] = __ldg(reinterpret_cast<const float4*>(wp + (size_t)(kb + 16 + j) * ldw));
+                }
             }
-            // four rows at a time: four independent FMA chains per lane
 #pragma unroll
             for (int r = 0; r < 16; r += 4) {
-                float4 a[4], b[4];
+                float4 a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = ld_smem4(zr + (r + i) * IS + kb);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    a[i] = ld_smem4(zr + (r + i) * IS + kg);
-                    b[i] = ld_smem4(zr + (r + i) * IS + kg + 4);
+                    const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[r + i][0] = fmaf(av[j], w[j].x, acc[r + i][0]);
+                        acc[r + i][1] = fmaf(av[j], w[j].y, acc[r + i][1]);
+                        acc[r + i][2] = fmaf(av[j], w[j].z, acc[r + i][2]);
+                        acc[r + i][3] = fmaf(av[j], w[j].w, acc[r + i][3]);
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].x, wc[0], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].y, wc[1], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].z, wc[2], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(a[i].w, wc[3], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].x, wc[4], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].y, wc[5], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].z, wc[6], acc[r + i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[r + i] = fmaf(b[i].w, wc[7], acc[r + i]);
             }
         }
-        float* op = out_s + ks * part_stride + (rt << 4) * OS + c;
+        float* op = out_s + ks * part_stride + (rt << 4) * OS + c4;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) op[r * OS] = acc[r];
+        for (int r = 0; r < 16; ++r) {
+            float4 v;
+            v.x = quad_sum(acc[r][0]);
+            v.y = quad_sum(acc[r][1]);
+            v.z = quad_sum(acc[r][2]);
+            v.w = quad_sum(acc[r][3]);
+            if ((r & 3) == qw) *reinterpret_cast<float4*>(op + r * OS) = v;
+        }
     }
 }
 
@@ -898,7 +917,8 @@ extern "C" int gpp_graph_filter_forward(const float* x, const void* S, int s_is_
     if (B == 0) return GPP_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (G == GF_C && F == GF_C && N <= GF_MAX_ROWS) {
-        GPP_REQUIRE(workspace, GPP_ERR_INVALID, "graph_filter_forward: workspace required");
+        GPP_REQUIRE(workspace && aligned16(workspace), GPP_ERR_INVALID,
+                    "graph_filter_forward: a 16-byte aligned workspace is required");
         const int mode = standalone_gf_mode();
         if (x_layout == GPP_NODE_MAJOR && y_layout == GPP_NODE_MAJOR && mode != 1 && gf_tc_tile_samples(N, K) > 0 &&
             (mode == 2 || (size_t)B * N >= 4096)) {
@@ -962,6 +982,8 @@ extern "C" int gpp_graph_filter_backward(const float* dy, const float* y, const 
     float* ws = reinterpret_cast<float*>(workspace);
     const bool need_w = dw || dbias;
     if (G == GF_C && F == GF_C && N <= GF_MAX_ROWS) {
+        GPP_REQUIRE(aligned16(w) && aligned16(workspace), GPP_ERR_INVALID,
+                    "graph_filter_backward: w and workspace must be 16-byte aligned");
         float* zbuf = ws;
         float* dyeff = zbuf + rows * K * GF_C;
         float* partial = dyeff + rows * GF_C;

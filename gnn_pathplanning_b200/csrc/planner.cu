@@ -413,7 +413,9 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         GPP_CUDA_OK(cudaEventRecord(e0, st));
     }
     int rc;
-    if (p->fe_mode == 2 || (p->fe_mode == 0 && rows >= 4096)) {
+    // auto = the register-tiled CUDA-core kernel at every size: it is 5-10 % faster than the tcgen05 kernel even at
+    // 40,960 agents per launch (profiles/r01_planner_microbench.txt); the tcgen05 kernel runs on request only
+    if (p->fe_mode == 2) {
         const float* imgs[6];
         for (int l = 0; l < 6; ++l) imgs[l] = A + p->off_fimg[l];
         rc = launch_feature_tc_kernel(fa, imgs, st);

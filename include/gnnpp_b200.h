@@ -197,8 +197,9 @@ int gpp_planner_wait(gpp_planner* p, unsigned long long ticket);
  * GPP_ERR_UNSUPPORTED at forward time if N/K do not fit its 128-row tile). */
 int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode);
 
-/* Which feature-extractor (CNN + compress MLP) kernel the planner uses: 0 = automatic, 1 = CUDA-core fp32
- * kernel (feature_kernel), 2 = tcgen05 3xTF32 implicit-GEMM kernel (feature_tc_kernel). */
+/* Which feature-extractor (CNN + compress MLP) kernel the planner uses: 0 = automatic (currently always the
+ * CUDA-core kernel, the faster one at every measured size), 1 = CUDA-core fp32 kernel (feature_kernel),
+ * 2 = tcgen05 3xTF32 implicit-GEMM kernel (feature_tc_kernel). */
 int gpp_planner_set_feature_mode(gpp_planner* p, int mode);
 
 /* Test hook for the tcgen05 plumbing: D[128][128] = A[128][32] . B[128][32]^T on the tensor cores
