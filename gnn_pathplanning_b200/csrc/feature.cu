@@ -69,8 +69,8 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------------
 // Filter stream of one agent tile.  Chunk sequence (k-major filters, row = ci*9 + tap, column = co):
-//   conv1: 4 chunks of 8 input channels per pass over the work items      (9 KB each)
-//   conv2: 8 chunks of 4 input channels per pass                          (9 KB)
+//   conv1: 2 chunks of 16 input channels per pass over the work items     (18 KB each)
+//   conv2: 4 chunks of 8 input channels per pass                          (18 KB)
 //   conv3: 8 chunks of 8 input channels                                   (18 KB)
 //   conv4: 16 chunks of 4 input channels                                  (18 KB)
 //   MLP  : 4 chunks, 8 inputs of each quarter of the input range          (4 x 4 KB)
@@ -87,7 +87,7 @@ struct WStream {
     uint32_t cons;      // chunks consumed since kernel start: slot = cons % RING_SLOTS, parity = (cons / RING_SLOTS) & 1
     uint32_t prod;      // chunks issued since kernel start
     int seq, seq_len;   // next chunk to issue / number of chunks of the current tile
-    int n1, n2;         // conv1 / conv2 chunks of the current tile (4 / 8 per pass)
+    int n1, n2;         // conv1 / conv2 chunks of the current tile (2 / 4 per pass)
 
     __device__ __forceinline__ void init(float* sm_base) {
         ring = sm_base + OFF_RING;
@@ -106,11 +106,11 @@ struct WStream {
             uint64_t* bar = full + slot;
             int i = seq;
             if (i < n1) {
-                mbar_arrive_expect_tx(bar, 9216u);
-                bulk_g2s(dst, A.w1t + (i & 3) * 2304, 9216u, bar);
+                mbar_arrive_expect_tx(bar, 18432u);
+                bulk_g2s(dst, A.w1t + (i & 1) * 4608, 18432u, bar);
             } else if ((i -= n1) < n2) {
-                mbar_arrive_expect_tx(bar, 9216u);
-                bulk_g2s(dst, A.w2t + (i & 7) * 2304, 9216u, bar);
+                mbar_arrive_expect_tx(bar, 18432u);
+                bulk_g2s(dst, A.w2t + (i & 3) * 4608, 18432u, bar);
             } else if ((i -= n2) < 8) {
                 mbar_arrive_expect_tx(bar, 18432u);
                 bulk_g2s(dst, A.w3t + i * 4608, 18432u, bar);
@@ -130,8 +130,8 @@ struct WStream {
     }
     // start of a tile: the ring is empty (every chunk of the previous tile was consumed)
     __device__ __forceinline__ void begin_tile(const FeArgs& A, int conv1_passes, int conv2_passes) {
-        n1 = 4 * conv1_passes;
-        n2 = 8 * conv2_passes;
+        n1 = 2 * conv1_passes;
+        n2 = 4 * conv2_passes;
         seq = 0;
         seq_len = n1 + n2 + 8 + 16 + 4;
 #pragma unroll 1
@@ -357,12 +357,15 @@ __global__ void __launch_bounds__(FE_THREADS, 1) feature_kernel(const FeArgs A) 
                     for (int j = 0; j < 5; ++j)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
-                for (int j = 0; j < 4; ++j) {
-                    const float* ws = wsm.acquire() + (2 * qw) * 9 * 32 + l8 * 4;
+                for (int j = 0; j < 2; ++j) {
+                    const float* ws = wsm.acquire() + (4 * qw) * 9 * 32 + l8 * 4;
                     if (live) {
-                        const float* ap = act1 + ((a * 32 + j * 8 + 2 * qw) * 7 + r0) * 8;
-                        if (rt < 2) conv1_chunk<2>(acc, ap, ws);
-                        else conv1_chunk<1>(acc, ap, ws);
+                        const float* ap = act1 + ((a * 32 + j * 16 + 4 * qw) * 7 + r0) * 8;
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {      // 4 of the chunk's 16 input channels, two at a time
+                            if (rt < 2) conv1_chunk<2>(acc, ap + h * 112, ws + h * 18 * 32);
+                            else conv1_chunk<1>(acc, ap + h * 112, ws + h * 18 * 32);
+                        }
                     }
                     wsm.release(A);
                 }
@@ -397,9 +400,13 @@ __global__ void __launch_bounds__(FE_THREADS, 1) feature_kernel(const FeArgs A) 
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
-            for (int j = 0; j < 8; ++j) {
-                const float* ws = wsm.acquire() + qw * 9 * 64 + co4;
-                if (live) conv2_chunk(acc, act2 + ((a * 32 + j * 4 + qw) * 7 + 2 * py) * 8, ws);
+            for (int j = 0; j < 4; ++j) {
+                const float* ws = wsm.acquire() + (2 * qw) * 9 * 64 + co4;
+                if (live) {
+                    const float* ap = act2 + ((a * 32 + j * 8 + 2 * qw) * 7 + 2 * py) * 8;
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) conv2_chunk(acc, ap + h * 56, ws + h * 9 * 64);
+                }
                 wsm.release(A);
             }
             if (live) {
