@@ -391,6 +391,157 @@ __global__ void conv3x3_bwd_weight_kernel(const float* __restrict__ dz, const fl
 }
 
 // ---------------------------------------------------------------------------------------
+// Row-tiled convolution kernels (H = 11, 5, 2 known at compile time).  A thread owns one output row (forward,
+// input gradient) or the 9 taps of one (co, ci) filter (weight gradient), keeps it in registers and reads whole
+// rows of its operands, so every loaded float feeds 3 (rows) to 4.5 (taps) FMAs instead of 0.5.  The order
+// of the fp32 additions into every output is exactly that of the one-output-per-thread kernels above
+// (ci/co outer, ky, kx; taps outside the map contribute fma(0, w, acc) = acc), so results are bit-identical.
+// ---------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(256) conv3x3_fwd_rows_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                               const float* __restrict__ b, float* __restrict__ out,
+                                                               int M, int Cin, int Cout) {
+    constexpr int HW = H * H;
+    const long long total = (long long)M * Cout * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i % H), co = (int)((i / H) % Cout);
+        const long long img = i / ((long long)H * Cout);
+        float acc[H];
+        const float bias = b[co];
+#pragma unroll
+        for (int x = 0; x < H; ++x) acc[x] = bias;
+        const float* ip = in + img * Cin * HW;
+        const float* wp = w + (size_t)co * Cin * 9;
+        for (int ci = 0; ci < Cin; ++ci) {
+            float wv[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wv[t] = wp[ci * 9 + t];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = y + ky - 1;
+                if (iy < 0 || iy >= H) continue;
+                float r[H + 2];
+                r[0] = 0.f;
+                r[H + 1] = 0.f;
+#pragma unroll
+                for (int x = 0; x < H; ++x) r[x + 1] = ip[ci * HW + iy * H + x];
+#pragma unroll
+                for (int x = 0; x < H; ++x) {
+                    float a = acc[x];
+                    if (x > 0) a = fmaf(r[x], wv[ky * 3], a);            // the skipped taps are the ones outside the map
+                    a = fmaf(r[x + 1], wv[ky * 3 + 1], a);
+                    if (x < H - 1) a = fmaf(r[x + 2], wv[ky * 3 + 2], a);
+                    acc[x] = a;
+                }
+            }
+        }
+        float* op = out + (img * Cout + co) * HW + y * H;
+#pragma unroll
+        for (int x = 0; x < H; ++x) op[x] = acc[x];
+    }
+}
+
+template <int H>
+__global__ void __launch_bounds__(256) conv3x3_bwd_input_rows_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                                     float* __restrict__ din, int M, int Cin, int Cout) {
+    constexpr int HW = H * H;
+    const long long total = (long long)M * Cin * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i % H), ci = (int)((i / H) % Cin);
+        const long long img = i / ((long long)H * Cin);
+        float acc[H];
+#pragma unroll
+        for (int x = 0; x < H; ++x) acc[x] = 0.f;
+        const float* dp = dz + img * Cout * HW;
+        for (int co = 0; co < Cout; ++co) {
+            const float* wp = w + ((size_t)co * Cin + ci) * 9;
+            float wv[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wv[t] = wp[t];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int oy = y + 1 - ky;
+                if (oy < 0 || oy >= H) continue;
+                float r[H + 2];
+                r[0] = 0.f;
+                r[H + 1] = 0.f;
+#pragma unroll
+                for (int x = 0; x < H; ++x) r[x + 1] = dp[co * HW + oy * H + x];
+#pragma unroll
+                for (int x = 0; x < H; ++x) {           // kx = 0, 1, 2 reads output column x + 1, x, x - 1
+                    float a = acc[x];
+                    if (x < H - 1) a = fmaf(r[x + 2], wv[ky * 3], a);
+                    a = fmaf(r[x + 1], wv[ky * 3 + 1], a);
+                    if (x > 0) a = fmaf(r[x], wv[ky * 3 + 2], a);
+                    acc[x] = a;
+                }
+            }
+        }
+        float* op = din + (img * Cin + ci) * HW + y * H;
+#pragma unroll
+        for (int x = 0; x < H; ++x) op[x] = acc[x];
+    }
+}
+
+// thread = (co, ci): all 9 taps over the images of chunk blockIdx.y; threads past Cout*Cin: bias sums
+template <int H>
+__global__ void __launch_bounds__(128) conv3x3_bwd_weight_taps_kernel(const float* __restrict__ dz, const float* __restrict__ in,
+                                                                      float* __restrict__ partial,
+                                                                      float* __restrict__ partial_b, int M, int Cin,
+                                                                      int Cout, int imgs_per_chunk) {
+    constexpr int HW = H * H;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m0 = blockIdx.y * imgs_per_chunk;
+    const int m1 = min(M, m0 + imgs_per_chunk);
+    const int nP = Cout * Cin;
+    if (i < nP) {
+        const int ci = i % Cin, co = i / Cin;
+        double acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t] = 0.0;
+        for (int img = m0; img < m1; ++img) {
+            const float* dp = dz + ((size_t)img * Cout + co) * HW;
+            const float* ip = in + ((size_t)img * Cin + ci) * HW;
+            float tsum[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) tsum[t] = 0.f;
+#pragma unroll
+            for (int y = 0; y < H; ++y) {
+                float d[H];
+#pragma unroll
+                for (int x = 0; x < H; ++x) d[x] = dp[y * H + x];
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int iy = y + ky - 1;
+                    if (iy < 0 || iy >= H) continue;         // compile-time after unrolling
+                    float r[H];
+#pragma unroll
+                    for (int x = 0; x < H; ++x) r[x] = ip[iy * H + x];
+#pragma unroll
+                    for (int x = 0; x < H; ++x) {
+                        if (x > 0) tsum[ky * 3] = fmaf(d[x], r[x - 1], tsum[ky * 3]);
+                        tsum[ky * 3 + 1] = fmaf(d[x], r[x], tsum[ky * 3 + 1]);
+                        if (x < H - 1) tsum[ky * 3 + 2] = fmaf(d[x], r[x + 1], tsum[ky * 3 + 2]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) acc[t] += (double)tsum[t];
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) partial[(size_t)blockIdx.y * nP * 9 + (size_t)i * 9 + t] = (float)acc[t];
+    } else if (i < nP + Cout) {
+        const int co = i - nP;
+        double acc = 0.0;
+        for (int img = m0; img < m1; ++img) {
+            const float* dp = dz + ((size_t)img * Cout + co) * HW;
+            for (int p = 0; p < HW; ++p) acc += (double)dp[p];
+        }
+        partial_b[(size_t)blockIdx.y * Cout + co] = (float)acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // workspace layout
 // ---------------------------------------------------------------------------------------
 struct TrainWs {
@@ -437,6 +588,35 @@ static inline int grid_for(long long total, int block = 256) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// the planner's maps are 11x11, 5x5 and 2x2: row-tiled kernels; anything else: the generic kernels
+static void launch_conv_fwd(const float* in, const float* w, const float* b, float* out, int M, int Cin, int Cout, int H,
+                            cudaStream_t st) {
+    const long long rows = (long long)M * Cout * H;
+    if (H == 11) conv3x3_fwd_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
+    else if (H == 5) conv3x3_fwd_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
+    else if (H == 2) conv3x3_fwd_rows_kernel<2><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
+    else conv3x3_fwd_kernel<<<grid_for(rows * H), 256, 0, st>>>(in, w, b, out, M, Cin, Cout, H);
+}
+static void launch_conv_bwd_input(const float* dz, const float* w, float* din, int M, int Cin, int Cout, int H,
+                                  cudaStream_t st) {
+    const long long rows = (long long)M * Cin * H;
+    if (H == 11) conv3x3_bwd_input_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
+    else if (H == 5) conv3x3_bwd_input_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
+    else if (H == 2) conv3x3_bwd_input_rows_kernel<2><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
+    else conv3x3_bwd_input_kernel<<<grid_for(rows * H), 256, 0, st>>>(dz, w, din, M, Cin, Cout, H);
+}
+static void launch_conv_bwd_weight(const float* dz, const float* in, float* partial, float* partial_b, int M, int Cin,
+                                   int Cout, int H, int imgs_per_chunk, int chunks, cudaStream_t st) {
+    const int nP = Cout * Cin;
+    const dim3 grid((nP + Cout + 127) / 128, chunks);
+    if (H == 11) conv3x3_bwd_weight_taps_kernel<11><<<grid, 128, 0, st>>>(dz, in, partial, partial_b, M, Cin, Cout, imgs_per_chunk);
+    else if (H == 5) conv3x3_bwd_weight_taps_kernel<5><<<grid, 128, 0, st>>>(dz, in, partial, partial_b, M, Cin, Cout, imgs_per_chunk);
+    else if (H == 2) conv3x3_bwd_weight_taps_kernel<2><<<grid, 128, 0, st>>>(dz, in, partial, partial_b, M, Cin, Cout, imgs_per_chunk);
+    else
+        conv3x3_bwd_weight_kernel<<<dim3((nP * 9 + Cout + 255) / 256, chunks), 256, 0, st>>>(dz, in, partial, partial_b, M, Cin,
+                                                                                         Cout, H, imgs_per_chunk);
+}
+
 }  // namespace gpp
 
 using namespace gpp;
@@ -461,7 +641,7 @@ extern "C" int gpp_planner_train_forward(const gpp_planner_weights* w, const gpp
         const long long total = (long long)M * Cout * HW;
         float* z = ws + L.z[l];
         float* a = ws + L.a[l];
-        conv3x3_fwd_kernel<<<grid_for(total), 256, 0, st>>>(in, w->conv_w[l], w->conv_b[l], z, M, Cin, Cout, H);
+        launch_conv_fwd(in, w->conv_w[l], w->conv_b[l], z, M, Cin, Cout, H, st);
         GPP_LAUNCH_CHECK();
         bn_stats_kernel<<<N * Cout, 128, 0, st>>>(z, ws + L.mean[l], ws + L.var[l], ws + L.invstd[l], B, N, Cout, HW, 1e-5f);
         GPP_LAUNCH_CHECK();
@@ -560,8 +740,7 @@ extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const fl
             const int ipc = (M + L.chunks - 1) / L.chunks;
             const int used = (M + ipc - 1) / ipc;
             const int nW = Cout * Cin * 9;
-            conv3x3_bwd_weight_kernel<<<dim3((nW + Cout + 255) / 256, used), 256, 0, st>>>(da, lin, ws + L.partial, ws + L.partial_b,
-                                                                                        M, Cin, Cout, H, ipc);
+            launch_conv_bwd_weight(da, lin, ws + L.partial, ws + L.partial_b, M, Cin, Cout, H, ipc, used, st);
             GPP_LAUNCH_CHECK();
             reduce_chunks_kernel<<<(nW + 255) / 256, 256, 0, st>>>(ws + L.partial, g->conv_w[l], used, nW);
             GPP_LAUNCH_CHECK();
@@ -569,7 +748,7 @@ extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const fl
             GPP_LAUNCH_CHECK();
         }
         if (l > 0) {
-            conv3x3_bwd_input_kernel<<<grid_for((long long)M * Cin * HW), 256, 0, st>>>(da, w->conv_w[l], dnext, M, Cin, Cout, H);
+            launch_conv_bwd_input(da, w->conv_w[l], dnext, M, Cin, Cout, H, st);
             GPP_LAUNCH_CHECK();
             float* t = dcur; dcur = dnext; dnext = t;
         }
@@ -584,9 +763,9 @@ extern "C" int gpp_debug_train_kernel(int op, const float* a, const float* b, co
                                       int Cin, int Cout, int H, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (op == 0) {
-        conv3x3_fwd_kernel<<<grid_for((long long)M * Cout * H * H), 256, 0, st>>>(a, b, c, out, M, Cin, Cout, H);
+        launch_conv_fwd(a, b, c, out, M, Cin, Cout, H, st);
     } else if (op == 1) {
-        conv3x3_bwd_input_kernel<<<grid_for((long long)M * Cin * H * H), 256, 0, st>>>(a, b, out, M, Cin, Cout, H);
+        launch_conv_bwd_input(a, b, out, M, Cin, Cout, H, st);
     } else if (op == 2) {
         const long long total = (long long)M * Cout * H * H;
         maxpool2_bwd_kernel<<<grid_for(total), 256, 0, st>>>(a, b, out, total, H, H / 2);
