@@ -483,6 +483,113 @@ __global__ void __launch_bounds__(256) conv3x3_bwd_input_rows_kernel(const float
     }
 }
 
+// 2x2 maps (conv3 / conv4): a row is only 2 pixels, so a thread owns the whole map of 4 consecutive images for one
+// output (forward) or input (input gradient) channel: 9 filter values + 4 float4 maps feed 64 FMAs.  Same order of
+// additions per output as above (channel outer, ky, kx, taps outside the map skipped).
+__global__ void __launch_bounds__(256) conv3x3_fwd_2x2_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ b, float* __restrict__ out,
+                                                              int M, int Cin, int Cout) {
+    const long long total = (long long)((M + 3) / 4) * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const int img0 = (int)(i / Cout) * 4;
+        const int nimg = min(4, M - img0);
+        float acc[4][4];
+        const float bias = b[co];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[j][p] = bias;
+        const float* wp = w + (size_t)co * Cin * 9;
+        for (int ci = 0; ci < Cin; ++ci) {
+            float wv[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wv[t] = wp[ci * 9 + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nimg) break;
+                const float4 v4 = *reinterpret_cast<const float4*>(in + ((size_t)(img0 + j) * Cin + ci) * 4);
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int y = 0; y < 2; ++y)
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        float a = acc[j][y * 2 + x];
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int iy = y + ky - 1;
+                            if (iy < 0 || iy > 1) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int ix = x + kx - 1;
+                                if (ix < 0 || ix > 1) continue;
+                                a = fmaf(v[iy * 2 + ix], wv[ky * 3 + kx], a);
+                            }
+                        }
+                        acc[j][y * 2 + x] = a;
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nimg) break;
+            *reinterpret_cast<float4*>(out + ((size_t)(img0 + j) * Cout + co) * 4) =
+                make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) conv3x3_bwd_input_2x2_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                                    float* __restrict__ din, int M, int Cin, int Cout) {
+    const long long total = (long long)((M + 3) / 4) * Cin;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin);
+        const int img0 = (int)(i / Cin) * 4;
+        const int nimg = min(4, M - img0);
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[j][p] = 0.f;
+        for (int co = 0; co < Cout; ++co) {
+            const float* wp = w + ((size_t)co * Cin + ci) * 9;
+            float wv[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) wv[t] = wp[t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j >= nimg) break;
+                const float4 v4 = *reinterpret_cast<const float4*>(dz + ((size_t)(img0 + j) * Cout + co) * 4);
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int y = 0; y < 2; ++y)
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        float a = acc[j][y * 2 + x];
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int oy = y + 1 - ky;
+                            if (oy < 0 || oy > 1) continue;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const int ox = x + 1 - kx;
+                                if (ox < 0 || ox > 1) continue;
+                                a = fmaf(v[oy * 2 + ox], wv[ky * 3 + kx], a);
+                            }
+                        }
+                        acc[j][y * 2 + x] = a;
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nimg) break;
+            *reinterpret_cast<float4*>(din + ((size_t)(img0 + j) * Cin + ci) * 4) =
+                make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        }
+    }
+}
+
 // thread = (co, ci): all 9 taps over the images of chunk blockIdx.y; threads past Cout*Cin: bias sums
 template <int H>
 __global__ void __launch_bounds__(128) conv3x3_bwd_weight_taps_kernel(const float* __restrict__ dz, const float* __restrict__ in,
@@ -594,6 +701,8 @@ static void launch_conv_fwd(const float* in, const float* w, const float* b, flo
     const long long rows = (long long)M * Cout * H;
     if (H == 11) conv3x3_fwd_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
     else if (H == 5) conv3x3_fwd_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
+    else if (H == 2 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0)
+        conv3x3_fwd_2x2_kernel<<<grid_for((long long)((M + 3) / 4) * Cout), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
     else if (H == 2) conv3x3_fwd_rows_kernel<2><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
     else conv3x3_fwd_kernel<<<grid_for(rows * H), 256, 0, st>>>(in, w, b, out, M, Cin, Cout, H);
 }
@@ -602,6 +711,8 @@ static void launch_conv_bwd_input(const float* dz, const float* w, float* din, i
     const long long rows = (long long)M * Cin * H;
     if (H == 11) conv3x3_bwd_input_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
     else if (H == 5) conv3x3_bwd_input_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
+    else if (H == 2 && ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(din)) & 15u) == 0)
+        conv3x3_bwd_input_2x2_kernel<<<grid_for((long long)((M + 3) / 4) * Cin), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
     else if (H == 2) conv3x3_bwd_input_rows_kernel<2><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
     else conv3x3_bwd_input_kernel<<<grid_for(rows * H), 256, 0, st>>>(dz, w, din, M, Cin, Cout, H);
 }

@@ -15,7 +15,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,Cin,Cout,H", [(40, 3, 32, 11), (160, 32, 32, 5), (80, 32, 64, 5), (640, 64, 64, 2),
-                                          (640, 64, 128, 2), (7, 5, 9, 4), (3, 2, 3, 7)])
+                                          (640, 64, 128, 2), (7, 64, 64, 2), (1, 3, 5, 2), (7, 5, 9, 4), (3, 2, 3, 7)])
 def test_conv_and_pool_kernels(M, Cin, Cout, H):
     from gnn_pathplanning_b200 import _lib
     lib = _lib.load()
