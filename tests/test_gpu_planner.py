@@ -74,8 +74,10 @@ def test_golden_train_step(golden, f):
             assert rel_err(sd_after[k[9:]].double().cpu().numpy(), g[k]) <= TOL, k
 
 
+# the last three: 3 / 6 / 4 agents per feature-kernel tile with a ragged last tile (1 / 2 / 2 agents)
 @pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (20, 3, 24, 28), (40, 3, 16, 50), (1, 2, 5, 8),
-                                         (64, 3, 3, 50), (10, 1, 9, 20), (3, 3, 301, 12)])
+                                         (64, 3, 3, 50), (10, 1, 9, 20), (3, 3, 301, 12),
+                                         (10, 3, 40, 20), (10, 3, 80, 20), (9, 3, 50, 20)])
 def test_eval_vs_oracle(N, K, B, map_w):
     from gnn_pathplanning_b200 import synthetic
     from oracle import planner_oracle as po
