@@ -22,12 +22,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def install_dropin() -> None:
-    """Prepends gnn_pathplanning_b200/dropin to sys.path so that
-    `from graphs.models.decentralplanner import *` and
-    `import utils.graphUtils.graphML as gml` (agents/decentralplannerlocal.py:27,
-    decentralplanner.py:9) pick up the B200 implementations."""
-    import os
-    import sys
-    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
-    if d not in sys.path:
-        sys.path.insert(0, d)
+    """Makes `from graphs.models.decentralplanner import *`, `import utils.graphUtils.graphML as gml`
+    and `from graphs.weights_initializer import weights_init` (agents/decentralplannerlocal.py:27,
+    decentralplanner.py:7,9) resolve to the B200 implementations through an import hook that
+    answers exactly those three names; every other `graphs.*` / `utils.*` module of the reference
+    (`utils.metrics`, `utils.multirobotsim_dcenlocal`, `graphs.losses.*` ...) keeps importing from
+    the reference tree."""
+    from . import dropin
+    dropin.install()

@@ -103,12 +103,29 @@ def test_per_agent_batchnorm_matches_reference_semantics():
         assert rel_err(after[k].double().numpy(), v.double().numpy()) <= 1e-6, k
 
 
-def test_dropin_names_resolve():
+def test_dropin_hook_routes_three_names_and_nothing_else(tmp_path):
+    """install_dropin() on a stand-in tree laid out like the reference (package __init__s that eagerly import
+    every sibling module, as /root/reference/utils/__init__.py:6-10 does): the three hot-path module names
+    resolve to this package, every other module of the same packages still comes from the tree."""
     import gnn_pathplanning_b200 as gp
     import sys
+    eager = ("import os, sys\npath = os.path.dirname(os.path.abspath(__file__))\n"
+             "for py in [f[:-3] for f in os.listdir(path) if f.endswith('.py') and f != '__init__.py']:\n"
+             "    __import__('.'.join([__name__, py]), fromlist=[py])\n")
+    tree = {"graphs/__init__.py": eager, "graphs/weights_initializer.py": "ORIGIN = 'tree'\n",
+            "graphs/models/__init__.py": eager, "graphs/models/decentralplanner.py": "ORIGIN = 'tree'\n",
+            "graphs/losses/__init__.py": eager, "graphs/losses/cross_entropy.py": "ORIGIN = 'tree'\n",
+            "utils/__init__.py": eager, "utils/metrics.py": "ORIGIN = 'tree'\n",
+            "utils/graphUtils/__init__.py": "", "utils/graphUtils/graphML.py": "ORIGIN = 'tree'\n",
+            "utils/graphUtils/graphTools.py": "ORIGIN = 'tree'\n"}
+    for rel, src in tree.items():
+        f = tmp_path / rel
+        f.parent.mkdir(parents=True, exist_ok=True)
+        f.write_text(src)
     saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("graphs", "utils")}
     for k in saved:
         del sys.modules[k]
+    sys.path.insert(0, str(tmp_path))
     try:
         gp.install_dropin()
         from graphs.models.decentralplanner import DecentralPlannerNet
@@ -117,7 +134,16 @@ def test_dropin_names_resolve():
         assert DecentralPlannerNet is gp.DecentralPlannerNet
         assert gml.GraphFilterBatch is gp.GraphFilterBatch and gml.BatchLSIGF is gp.BatchLSIGF
         assert weights_init is gp.weights_init
+        import graphs.losses.cross_entropy as ce
+        import utils.metrics as metrics
+        import utils.graphUtils.graphTools as gt
+        assert ce.ORIGIN == metrics.ORIGIN == gt.ORIGIN == "tree"
+        import graphs
+        assert graphs.weights_initializer.weights_init is gp.weights_init      # the eager __init__ got the override too
     finally:
+        from gnn_pathplanning_b200 import dropin
+        dropin.uninstall()
+        sys.path.remove(str(tmp_path))
         for k in [k for k in sys.modules if k.split(".")[0] in ("graphs", "utils")]:
             del sys.modules[k]
         sys.modules.update(saved)
