@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libgnnpp_b200.so")
 SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "feature.cu", "feature_tc.cu", "train.cu", "planner.cu")
 HEADERS = ("common.cuh", "feature.cuh", "tc_common.cuh")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200.h")
+INCLUDE_DEBUG = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200_debug.h")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -37,11 +38,15 @@ EXPORTED = (
     "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
     "gpp_planner_forward", "gpp_planner_forward_host",
     "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward",
-    "gpp_planner_forward_host_async", "gpp_planner_wait", "gpp_debug_tc_timing", "gpp_debug_gf_timing",
-    "gpp_debug_feature_tc_timing", "gpp_debug_feature_timing", "gpp_debug_train_kernel",
+    "gpp_planner_forward_host_async", "gpp_planner_wait",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
-    "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode", "gpp_debug_umma_selftest",
+    "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode",
     "gpp_launch_count", "gpp_reset_launch_count",
+)
+# test / profiling hooks declared in include/gnnpp_b200_debug.h (not part of the drop-in boundary)
+DEBUG_EXPORTED = (
+    "gpp_debug_set_option", "gpp_debug_umma_selftest", "gpp_debug_tc_timing", "gpp_debug_gf_timing",
+    "gpp_debug_feature_tc_timing", "gpp_debug_feature_timing", "gpp_debug_train_kernel",
 )
 
 
@@ -70,25 +75,53 @@ class PlannerGrads(C.Structure):
     ]
 
 
-def _stale() -> bool:
-    if not os.path.isfile(LIB_PATH):
+OBJ_DIR = os.path.join(CSRC_DIR, "build")
+
+
+def _newer(path: str, deps) -> bool:
+    """True if `path` is missing or older than any dependency."""
+    if not os.path.isfile(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC_DIR, s) for s in SOURCES + HEADERS] + [INCLUDE]
+    t = os.path.getmtime(path)
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
+def _stale() -> bool:
+    deps = [os.path.join(CSRC_DIR, s) for s in SOURCES + HEADERS] + [INCLUDE, INCLUDE_DEBUG]
+    return _newer(LIB_PATH, deps)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compiles the CUDA sources for sm_100a into the in-tree shared library."""
+    """Compiles the CUDA sources for sm_100a into the in-tree shared library: one nvcc -c per
+    translation unit (in parallel, only the stale ones), then one link."""
     if not force and not _stale():
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdrs = [os.path.join(CSRC_DIR, h) for h in HEADERS] + [INCLUDE, INCLUDE_DEBUG]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, src[:-3] + ".o")
+        path = os.path.join(CSRC_DIR, src)
+        if force or _newer(obj, [path] + hdrs):
+            cmd = [nvcc] + flags + ["-c", "-o", obj, path]
+            if verbose:
+                print(" ".join(cmd))
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (r.stdout, r.stderr))
+        raise RuntimeError("nvcc link failed:\n%s\n%s" % (r.stdout, r.stderr))
     return LIB_PATH
 
 
@@ -162,6 +195,10 @@ def load():
         lib.gpp_planner_set_graph_filter_mode.argtypes = [vp, i]
         lib.gpp_planner_set_feature_mode.restype = i
         lib.gpp_planner_set_feature_mode.argtypes = [vp, i]
+        lib.gpp_debug_set_option.restype = i
+        lib.gpp_debug_set_option.argtypes = [C.c_char_p, i]
+        lib.gpp_debug_train_kernel.restype = i
+        lib.gpp_debug_train_kernel.argtypes = [i, vp, vp, vp, vp, i, i, i, i, vp]
         lib.gpp_debug_umma_selftest.restype = i
         lib.gpp_debug_umma_selftest.argtypes = [vp, vp, vp, vp]
         lib.gpp_launch_count.restype = C.c_ulonglong
@@ -181,6 +218,11 @@ def check(rc: int) -> None:
     if rc == GPP_ERR_UNSUPPORTED:
         raise NotImplementedError("libgnnpp_b200: " + msg)
     raise RuntimeError("libgnnpp_b200 (status %d): %s" % (rc, msg))
+
+
+def set_debug_option(name: str, value: int) -> None:
+    """Process-wide debug switch of the library (include/gnnpp_b200_debug.h)."""
+    check(load().gpp_debug_set_option(name.encode(), int(value)))
 
 
 def launch_count() -> int:

@@ -37,7 +37,28 @@ extern thread_local unsigned long long g_launches;
         GPP_CUDA_OK(cudaGetLastError());                                                   \
     } while (0)
 
-int sm_count();
+int sm_count();       // SM count of the CURRENT device (cached per device ordinal)
+
+// Debug switches (include/gnnpp_b200_debug.h: gpp_debug_set_option); all 0 in production.
+enum DebugOption { DBG_GF_TIMING = 0, DBG_TC_TIMING = 1, DBG_FE_TIMING = 2, DBG_NO_PDL = 3, DBG_GF_MODE = 4, DBG_COUNT = 5 };
+int debug_option(int which);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device function attribute: remember the largest
+// value configured per device ordinal instead of one process-wide flag.
+constexpr int kMaxDevices = 64;
+struct SmemConfig {
+    size_t bytes[kMaxDevices] = {};
+};
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, SmemConfig& cfg, size_t smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < kMaxDevices && cfg.bytes[dev] >= smem) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) cfg.bytes[dev] = smem;
+    return e;
+}
 
 // Launch with (pdl != 0) or without the programmatic-stream-serialization attribute.
 template <typename Kernel, typename Args>

@@ -567,19 +567,15 @@ int debug_feature_timing(unsigned long long* out7) {
 
 int launch_feature_kernel(const FeArgs& fa_in, cudaStream_t st) {
     FeArgs fa = fa_in;
-    static bool configured = false;
-    if (!configured) {
-        GPP_CUDA_OK(cudaFuncSetAttribute(feature_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)FE_SMEM_BYTES));
-        configured = true;
-    }
+    static SmemConfig smem_cfg;
+    GPP_CUDA_OK(ensure_dynamic_smem(feature_kernel, smem_cfg, FE_SMEM_BYTES));
     int apt = (fa.total_agents + sm_count() - 1) / sm_count();
     if (apt > AM) apt = AM;
     if (apt < 1) apt = 1;
     fa.apt = apt;
     fa.num_tiles = (fa.total_agents + apt - 1) / apt;
     fa.timing = nullptr;
-    if (getenv("GPP_FE_TIMING")) {
+    if (debug_option(DBG_FE_TIMING)) {
         if (!g_fe_timing) {
             GPP_CUDA_OK(cudaMalloc(&g_fe_timing, 64));
             GPP_CUDA_OK(cudaMemset(g_fe_timing, 0, 64));

@@ -428,15 +428,12 @@ int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStr
     a.apt = apt;
     a.num_tiles = (fa.total_agents + apt - 1) / apt;
     a.timing = nullptr;
-    if (getenv("GPP_TC_TIMING")) {
+    if (debug_option(DBG_TC_TIMING)) {
         if (!g_ft_timing) { cudaMalloc(&g_ft_timing, 256); cudaMemset(g_ft_timing, 0, 256); }
         a.timing = g_ft_timing;
     }
-    static bool configured = false;
-    if (!configured) {
-        GPP_CUDA_OK(cudaFuncSetAttribute(feature_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
-        configured = true;
-    }
+    static SmemConfig smem_cfg;
+    GPP_CUDA_OK(ensure_dynamic_smem(feature_tc_kernel, smem_cfg, FT_SMEM_BYTES));
     const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
     feature_tc_kernel<<<grid, FT_THREADS + 32, FT_SMEM_BYTES, st>>>(a);
     GPP_LAUNCH_CHECK();

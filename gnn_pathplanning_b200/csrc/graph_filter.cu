@@ -844,7 +844,7 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
     a.lpart = lpart;
     a.tickets = tickets;
     a.timing = nullptr;
-    if (getenv("GPP_GF_TIMING")) {
+    if (debug_option(DBG_GF_TIMING)) {
         if (!g_gf_timing) {
             GPP_CUDA_OK(cudaMalloc(&g_gf_timing, 64));
             GPP_CUDA_OK(cudaMemset(g_gf_timing, 0, 64));
@@ -856,12 +856,8 @@ int launch_gf_forward_fast(const float* x, const void* S, int s_is_f64, const fl
     a.w_smem = (a.csplit == 2 && wsplit && GfFwdSmem(N, K, a.TS, 2, 1).total() <= 220 * 1024) ? 1 : 0;
     const GfFwdSmem L(N, K, a.TS, a.csplit, a.w_smem);
     const size_t smem = L.total();
-    static size_t configured = 0;
-    if (smem > configured) {
-        GPP_CUDA_OK(cudaFuncSetAttribute(gf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-        configured = smem;
-    }
+    static SmemConfig smem_cfg;
+    GPP_CUDA_OK(ensure_dynamic_smem(gf_fwd_kernel, smem_cfg, smem));
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_fwd_kernel, GF_FWD_THREADS, smem) != cudaSuccess ||
         per_sm < 1) {
@@ -886,15 +882,8 @@ int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const floa
                          float* y, const float* wa, const float* ba, float* logits, int B, int N, int K,
                          int relu, int allow_bulk, cudaStream_t st);
 
-// GPP_GF_MODE environment override for the standalone op: 0 auto, 1 CUDA-core, 2 tensor-core
-static int standalone_gf_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("GPP_GF_MODE");
-        mode = (e && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 0;
-    }
-    return mode;
-}
+// debug override for the standalone op (gpp_debug_set_option("gf_mode", m)): 0 auto, 1 CUDA-core, 2 tcgen05
+static int standalone_gf_mode() { return debug_option(DBG_GF_MODE); }
 }  // namespace gpp
 
 using namespace gpp;
@@ -999,12 +988,8 @@ extern "C" int gpp_graph_filter_backward(const float* dy, const float* y, const 
         a.s_is_f64 = s_is_f64; a.x_layout = x_layout; a.y_layout = y_layout; a.relu = fuse_relu;
         const GfBwdSmem L(N, K, a.TS);
         const size_t smem = L.total();
-        static size_t configured = 0;
-        if (smem > configured) {
-            GPP_CUDA_OK(cudaFuncSetAttribute(gf_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-            configured = smem;
-        }
+        static SmemConfig smem_cfg;
+        GPP_CUDA_OK(ensure_dynamic_smem(gf_bwd_data_kernel, smem_cfg, smem));
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 4) per_sm = 4;

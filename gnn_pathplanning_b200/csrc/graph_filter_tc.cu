@@ -489,18 +489,15 @@ int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const floa
     a.num_tiles = (B + a.TS - 1) / a.TS;
     a.s_is_f64 = s_is_f64; a.relu = relu;
     a.timing = nullptr;
-    if (getenv("GPP_TC_TIMING")) {
+    if (debug_option(DBG_TC_TIMING)) {
         static unsigned long long* dbuf = nullptr;
         if (!dbuf) { cudaMalloc(&dbuf, 64); cudaMemset(dbuf, 0, 64); }
         a.timing = dbuf;
         g_tc_timing = dbuf;
     }
     const size_t smem = GfTcSmem(N, K, a.TS).total();
-    static size_t configured = 0;
-    if (smem > configured) {
-        GPP_CUDA_OK(cudaFuncSetAttribute(gf_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemConfig smem_cfg;
+    GPP_CUDA_OK(ensure_dynamic_smem(gf_fwd_tc_kernel, smem_cfg, smem));
     const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
     gf_fwd_tc_kernel<<<grid, TC_THREADS + 32, smem, st>>>(a);
     GPP_LAUNCH_CHECK();

@@ -7,6 +7,7 @@
 // plus the one-off parameter re-layout (k-major filters, eval BatchNorm folded to scale/shift).
 #include "common.cuh"
 #include "feature.cuh"
+#include "../../include/gnnpp_b200_debug.h"
 
 #include <stdarg.h>
 #include <string.h>
@@ -27,15 +28,18 @@ void set_error(const char* fmt, ...) {
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
-    }
+    static int cached[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < kMaxDevices && cached[dev] > 0) return cached[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < kMaxDevices) cached[dev] = n;
     return n;
 }
+
+static int g_debug_options[DBG_COUNT] = {};
+int debug_option(int which) { return (which >= 0 && which < DBG_COUNT) ? g_debug_options[which] : 0; }
 
 // internal launchers from graph_filter.cu
 int launch_transpose_taps(const float* w, float* wt, int F, int KG, cudaStream_t st);
@@ -109,6 +113,10 @@ constexpr int kStageSlots = 3;   // device staging slots of the pipelined host-b
 
 struct gpp_planner {
     int K;
+    int device;          // CUDA device ordinal the handle (arena, scratch, streams) lives on
+    cudaStream_t last_stream;    // stream of the most recent forward / weight staging: a call on another stream first
+    bool last_stream_valid;      // waits for it (the feature workspace and the filter's scratch are shared per handle)
+    cudaEvent_t order_event;
     float* arena;        // prepared weights
     size_t off_w[6];     // conv0..4 k-major, compress k-major
     size_t off_sc[5], off_sh[5];
@@ -178,6 +186,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     gpp_planner* p = new gpp_planner();
     memset(p, 0, sizeof(*p));
     p->K = K;
+    if (cudaGetDevice(&p->device) != cudaSuccess) p->device = 0;
     size_t off = 0;
     auto take = [&](size_t n) { size_t o = off; off += (n + 63) / 64 * 64; return o; };
     for (int l = 0; l < 5; ++l) p->off_w[l] = take((size_t)kConvC[l] * 9 * kConvC[l + 1]);
@@ -217,6 +226,7 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->d_S);
     cudaFree(p->d_logits);
     if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->order_event) cudaEventDestroy(p->order_event);
     for (int i = 0; i < 16; ++i)
         if (p->tickets[i]) cudaEventDestroy(p->tickets[i]);
     for (int i = 0; i < kStageSlots; ++i) {
@@ -241,6 +251,19 @@ extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
 // debug: per-layer {staging loop, wait for MMAs, epilogue} cycle totals of feature_tc_kernel + tiles at [18]
 extern "C" int gpp_debug_feature_tc_timing(unsigned long long* out20) { return debug_feature_tc_timing(out20); }
 extern "C" int gpp_debug_feature_timing(unsigned long long* out7) { return debug_feature_timing(out7); }
+
+// debug switches (include/gnnpp_b200_debug.h)
+extern "C" int gpp_debug_set_option(const char* name, int value) {
+    GPP_REQUIRE(name, GPP_ERR_INVALID, "debug_set_option: null name");
+    static const char* const names[DBG_COUNT] = {"gf_timing", "tc_timing", "fe_timing", "no_pdl", "gf_mode"};
+    for (int i = 0; i < DBG_COUNT; ++i)
+        if (strcmp(name, names[i]) == 0) {
+            g_debug_options[i] = value;
+            return GPP_OK;
+        }
+    set_error("debug_set_option: unknown option '%s'", name);
+    return GPP_ERR_INVALID;
+}
 
 extern "C" int gpp_planner_set_feature_mode(gpp_planner* p, int mode) {
     GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_feature_mode: mode must be 0, 1 or 2");
@@ -284,10 +307,41 @@ static cudaEvent_t next_event(gpp_planner* p) {
     return (*p->events)[p->events_used++];
 }
 
+// Every entry point runs on the handle's device, whatever device the calling thread had current.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
+// The handle's scratch (feature workspace, split-filter tickets / partial logits, weight arena) is shared by all
+// calls; calls on ONE stream are ordered by the stream.  When the stream changes, the new stream waits for
+// everything submitted so far on the previous one (recorded lazily, so the steady state pays nothing).
+static int order_after_previous_stream(gpp_planner* p, cudaStream_t st) {
+    if (p->last_stream_valid && p->last_stream != st) {
+        if (!p->order_event) GPP_CUDA_OK(cudaEventCreateWithFlags(&p->order_event, cudaEventDisableTiming));
+        GPP_CUDA_OK(cudaEventRecord(p->order_event, p->last_stream));
+        GPP_CUDA_OK(cudaStreamWaitEvent(st, p->order_event, 0));
+    }
+    p->last_stream = st;
+    p->last_stream_valid = true;
+    return GPP_OK;
+}
+
 extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights* w, int on_device,
                                        void* stream) {
     GPP_REQUIRE(p && w, GPP_ERR_INVALID, "planner_set_weights: null pointer");
+    DeviceGuard guard(p->device);
     cudaStream_t st = on_device ? reinterpret_cast<cudaStream_t>(stream) : p->stream;
+    {   // outstanding forwards on another stream still read the arena
+        int rc0 = order_after_previous_stream(p, st);
+        if (rc0) return rc0;
+    }
     gpp_planner_weights d = *w;
     const int K = p->K;
     if (!on_device) {
@@ -356,27 +410,26 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     return GPP_OK;
 }
 
-static int ensure_feat(gpp_planner* p, size_t rows) {
+// Growing a workspace: stream-ordered free + allocation on the launching stream (the callers have already ordered
+// `st` after any other stream that used the handle), so no device-wide synchronisation on the step path.
+static int ensure_feat(gpp_planner* p, size_t rows, cudaStream_t st) {
     if (p->feat_rows >= rows) return GPP_OK;
-    // growing the workspace must not race with kernels still using the old one
-    GPP_CUDA_OK(cudaDeviceSynchronize());
-    cudaFree(p->feat);
+    if (p->feat) GPP_CUDA_OK(cudaFreeAsync(p->feat, st));
     p->feat = nullptr;
     p->feat_rows = 0;
-    GPP_CUDA_OK(cudaMalloc(&p->feat, sizeof(float) * 128 * rows));
+    GPP_CUDA_OK(cudaMallocAsync(&p->feat, sizeof(float) * 128 * rows, st));
     p->feat_rows = rows;
     return GPP_OK;
 }
 
-static int ensure_gf_scratch(gpp_planner* p, size_t rows) {
+static int ensure_gf_scratch(gpp_planner* p, size_t rows, cudaStream_t st) {
     if (p->gf_lpart_rows >= rows) return GPP_OK;
-    GPP_CUDA_OK(cudaDeviceSynchronize());
-    cudaFree(p->gf_lpart);
+    if (p->gf_lpart) GPP_CUDA_OK(cudaFreeAsync(p->gf_lpart, st));
     p->gf_lpart = nullptr;
     p->gf_lpart_rows = 0;
     const size_t floats = (size_t)(2 * 5 + 1) * rows;
-    GPP_CUDA_OK(cudaMalloc(&p->gf_lpart, sizeof(float) * floats));
-    GPP_CUDA_OK(cudaMemset(p->gf_lpart, 0, sizeof(float) * floats));  // tickets start (and are left) at zero
+    GPP_CUDA_OK(cudaMallocAsync(&p->gf_lpart, sizeof(float) * floats, st));
+    GPP_CUDA_OK(cudaMemsetAsync(p->gf_lpart, 0, sizeof(float) * floats, st));  // tickets start (and are left) at zero
     p->gf_lpart_rows = rows;
     return GPP_OK;
 }
@@ -387,9 +440,13 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
                                 float* logits, float* features_out, int B, int N, int allow_bulk,
                                 cudaStream_t st) {
     const size_t rows = (size_t)B * N;
+    {
+        int rc0 = order_after_previous_stream(p, st);
+        if (rc0) return rc0;
+    }
     float* feat = features_out;
     if (!feat) {
-        int rc = ensure_feat(p, rows);
+        int rc = ensure_feat(p, rows, st);
         if (rc) return rc;
         feat = p->feat;
     }
@@ -398,8 +455,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     fa.x = x; fa.feat = feat; fa.total_agents = (int)rows; fa.apt = 0; fa.num_tiles = 0; fa.timing = nullptr;
     // programmatic dependent launch: each kernel's prologue (barriers, filter prefetch) overlaps the tail of the
     // kernel before it; not for the first forward after the weights changed (the prologue reads them)
-    static const bool pdl_env = getenv("GPP_NO_PDL") == nullptr;
-    const int pdl = (pdl_env && p->pdl_ok && !p->profiling) ? 1 : 0;
+    const int pdl = (!debug_option(DBG_NO_PDL) && p->pdl_ok && !p->profiling) ? 1 : 0;
     fa.pdl = pdl;
     fa.w0t = A + p->off_w[0]; fa.w1t = A + p->off_w[1]; fa.w2t = A + p->off_w[2];
     fa.w3t = A + p->off_w[3]; fa.w4t = A + p->off_w[4]; fa.w5t = A + p->off_w[5];
@@ -432,7 +488,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         rc = launch_gf_forward_tc(feat, S, s_is_f64, A + p->off_gfimg, A + p->off_gfb, nullptr, A + p->off_wa,
                                   A + p->off_ba, logits, B, N, p->K, 1, allow_bulk, st);
     else {
-        rc = ensure_gf_scratch(p, rows);
+        rc = ensure_gf_scratch(p, rows, st);
         if (rc) return rc;
         rc = launch_gf_forward_fast(feat, S, s_is_f64, A + p->off_gfw, A + p->off_gfb, nullptr,
                                     A + p->off_wa, A + p->off_ba, logits, B, N, p->K, GPP_NODE_MAJOR,
@@ -449,6 +505,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
 extern "C" int gpp_planner_forward(gpp_planner* p, const float* x, const void* S, int s_is_f64,
                                    float* logits, float* features_out, int B, int N, void* stream) {
     GPP_REQUIRE(p && x && S && logits, GPP_ERR_INVALID, "planner_forward: null pointer");
+    DeviceGuard guard(p->device);
     GPP_REQUIRE((reinterpret_cast<uintptr_t>(features_out) & 15) == 0, GPP_ERR_INVALID,
                 "planner_forward: features_out must be 16-byte aligned");
     GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward: gpp_planner_set_weights not called");
@@ -489,6 +546,7 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
                                               int s_is_f64, float* logits_host, int B, int N,
                                               unsigned long long* ticket) {
     GPP_REQUIRE(p && x_host && S_host && logits_host && ticket, GPP_ERR_INVALID, "planner_forward_host_async: null pointer");
+    DeviceGuard guard(p->device);
     GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward_host_async: gpp_planner_set_weights not called");
     GPP_REQUIRE(B >= 1 && N >= 1 && N <= 64, GPP_ERR_INVALID, "planner_forward_host_async: bad sizes B=%d N=%d", B, N);
     void* mx = mapped_alias_cached(p, x_host);
@@ -551,6 +609,7 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
 
 extern "C" int gpp_planner_wait(gpp_planner* p, unsigned long long ticket) {
     GPP_REQUIRE(p, GPP_ERR_INVALID, "planner_wait: null planner");
+    DeviceGuard guard(p->device);
     GPP_REQUIRE(ticket < p->next_ticket && ticket + 16 >= p->next_ticket, GPP_ERR_INVALID,
                 "planner_wait: ticket %llu is not among the 16 most recent calls", ticket);
     GPP_CUDA_OK(cudaEventSynchronize(p->tickets[ticket % 16]));
@@ -560,6 +619,7 @@ extern "C" int gpp_planner_wait(gpp_planner* p, unsigned long long ticket) {
 extern "C" int gpp_planner_forward_host(gpp_planner* p, const float* x_host, const void* S_host,
                                         int s_is_f64, float* logits_host, int B, int N) {
     GPP_REQUIRE(p && x_host && S_host && logits_host, GPP_ERR_INVALID, "planner_forward_host: null pointer");
+    DeviceGuard guard(p->device);
     GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward_host: gpp_planner_set_weights not called");
     GPP_REQUIRE(B >= 0 && N >= 1, GPP_ERR_INVALID, "planner_forward_host: bad sizes B=%d N=%d", B, N);
     GPP_REQUIRE(N <= 64, GPP_ERR_UNSUPPORTED, "planner_forward_host: N=%d > 64 agents", N);

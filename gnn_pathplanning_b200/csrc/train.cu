@@ -869,7 +869,7 @@ extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const fl
 
 // debug: single training kernels for unit tests (tests/ only)
 //   op 0: conv3x3_fwd (a = in, b = w, c = bias)      op 1: conv3x3_bwd_input (a = dz, b = w)
-//   op 2: maxpool2_bwd (a = act, b = dp)
+//   op 2: maxpool2_bwd (a = act, b = dp)           op 3: conv3x3 weight/bias gradient (a = dz, b = in) -> dW | db
 extern "C" int gpp_debug_train_kernel(int op, const float* a, const float* b, const float* c, float* out, int M,
                                       int Cin, int Cout, int H, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -880,6 +880,22 @@ extern "C" int gpp_debug_train_kernel(int op, const float* a, const float* b, co
     } else if (op == 2) {
         const long long total = (long long)M * Cout * H * H;
         maxpool2_bwd_kernel<<<grid_for(total), 256, 0, st>>>(a, b, out, total, H, H / 2);
+    } else if (op == 3) {
+        // conv weight + bias gradient exactly as the training step computes it: per-chunk partial sums, then the
+        // fixed-order chunk reduction.  out = dW [Cout][Cin][3][3] followed by db [Cout].
+        const int chunks = M < 64 ? M : 64;
+        const int ipc = (M + chunks - 1) / chunks;
+        const int used = (M + ipc - 1) / ipc;
+        const int nW = Cout * Cin * 9;
+        float* scratch = nullptr;
+        GPP_CUDA_OK(cudaMallocAsync(&scratch, sizeof(float) * ((size_t)used * nW + (size_t)used * Cout), st));
+        float* partial_b = scratch + (size_t)used * nW;
+        launch_conv_bwd_weight(a, b, scratch, partial_b, M, Cin, Cout, H, ipc, used, st);
+        GPP_LAUNCH_CHECK();
+        reduce_chunks_kernel<<<(nW + 255) / 256, 256, 0, st>>>(scratch, out, used, nW);
+        GPP_LAUNCH_CHECK();
+        reduce_chunks_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(partial_b, out + nW, used, Cout);
+        GPP_CUDA_OK(cudaFreeAsync(scratch, st));
     } else {
         set_error("debug_train_kernel: unknown op %d", op);
         return GPP_ERR_INVALID;

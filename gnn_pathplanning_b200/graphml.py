@@ -27,8 +27,8 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
             "and does not fall back to the CPU" % (name, t.device))
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
 
 
 def _gso3(S: torch.Tensor) -> torch.Tensor:
@@ -54,10 +54,11 @@ class _GraphFilterFn(torch.autograd.Function):
         y = torch.empty(yshape, device=x.device, dtype=torch.float32)
         ws_bytes = lib.gpp_graph_filter_workspace_bytes(G, F_out, K)
         ws = torch.empty(max(ws_bytes, 4) // 4, device=x.device, dtype=torch.float32)
-        _lib.check(lib.gpp_graph_filter_forward(
-            xc.data_ptr(), S.data_ptr(), int(S.dtype == torch.float64), wc.data_ptr(),
-            bc.data_ptr() if bc is not None else None, y.data_ptr(),
-            B, N, G, F_out, K, x_layout, y_layout, int(fuse_relu), ws.data_ptr(), _stream_ptr()))
+        with torch.cuda.device(x.device):
+            _lib.check(lib.gpp_graph_filter_forward(
+                xc.data_ptr(), S.data_ptr(), int(S.dtype == torch.float64), wc.data_ptr(),
+                bc.data_ptr() if bc is not None else None, y.data_ptr(),
+                B, N, G, F_out, K, x_layout, y_layout, int(fuse_relu), ws.data_ptr(), _stream_ptr(x.device)))
         ctx.save_for_backward(xc, S, wc, y if fuse_relu else None)
         ctx.cfg = (B, N, G, F_out, K, x_layout, y_layout, int(fuse_relu), bias is not None)
         return y
@@ -74,13 +75,14 @@ class _GraphFilterFn(torch.autograd.Function):
         db = torch.empty(F_out, device=xc.device, dtype=torch.float32) if (need_b and has_bias) else None
         ws_bytes = lib.gpp_graph_filter_backward_workspace_bytes(B, N, G, F_out, K)
         ws = torch.empty(max(ws_bytes, 4) // 4, device=xc.device, dtype=torch.float32)
-        _lib.check(lib.gpp_graph_filter_backward(
-            dyc.data_ptr(), y.data_ptr() if y is not None else None, xc.data_ptr(), S.data_ptr(),
-            int(S.dtype == torch.float64), wc.data_ptr(),
-            dx.data_ptr() if dx is not None else None,
-            dw.data_ptr() if dw is not None else None,
-            db.data_ptr() if db is not None else None,
-            B, N, G, F_out, K, x_layout, y_layout, fuse_relu, ws.data_ptr(), _stream_ptr()))
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.gpp_graph_filter_backward(
+                dyc.data_ptr(), y.data_ptr() if y is not None else None, xc.data_ptr(), S.data_ptr(),
+                int(S.dtype == torch.float64), wc.data_ptr(),
+                dx.data_ptr() if dx is not None else None,
+                dw.data_ptr() if dw is not None else None,
+                db.data_ptr() if db is not None else None,
+                B, N, G, F_out, K, x_layout, y_layout, fuse_relu, ws.data_ptr(), _stream_ptr(xc.device)))
         return dx, None, dw, (db.reshape(F_out, 1) if db is not None else None), None, None, None
 
 
@@ -100,7 +102,23 @@ def graph_filter(x, S, weight, bias=None, fuse_relu=False, x_layout=FEATURE_MAJO
     _require_cuda(weight, "weight")
     if x.dtype != torch.float32 or weight.dtype != torch.float32:
         raise TypeError("gnn_pathplanning_b200: x and weight must be float32")
-    return _GraphFilterFn.apply(x, _gso3(S), weight, bias, bool(fuse_relu), x_layout, y_layout)
+    S3 = _gso3(S)
+    # the reference fails an assert (graphML.py:2325-2330) or a reshape on inconsistent shapes; raw pointers
+    # must never see them
+    F_out, _, K, G = weight.shape
+    N = S3.shape[-1]
+    assert x.dim() == 3 and S3.dim() == 3 and S3.shape[1] == N
+    assert S3.shape[0] == x.shape[0], "GSO batch %d != signal batch %d" % (S3.shape[0], x.shape[0])
+    if x_layout == FEATURE_MAJOR:
+        assert x.shape[1] == G and x.shape[2] == N
+    else:
+        assert x.shape[1] == N and x.shape[2] == G
+    if bias is not None:
+        assert bias.numel() == F_out
+        _require_cuda(bias, "bias")
+    assert S3.device == x.device and weight.device == x.device and (bias is None or bias.device == x.device), \
+        "x, S, weight and bias must live on the same device"
+    return _GraphFilterFn.apply(x, S3, weight, bias, bool(fuse_relu), x_layout, y_layout)
 
 
 def BatchLSIGF(h, S, x, b=None):
@@ -153,6 +171,7 @@ class GraphFilterBatch(nn.Module):
     def forward(self, x, fuse_relu=False):
         B, G, Nin = x.shape
         assert G == self.G
+        assert self.S is not None and self.S.shape[0] == B and Nin <= self.N
         if Nin < self.N:
             x = torch.cat((x, torch.zeros(B, G, self.N - Nin, dtype=x.dtype, device=x.device)), dim=2)
         u = graph_filter(x, self.S, self.weight, self.bias, fuse_relu)

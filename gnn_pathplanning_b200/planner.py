@@ -15,7 +15,7 @@ Execution:
     torch.autograd.Function around the whole network): all B*N agents batched, the
     reference's PER-AGENT BatchNorm statistics and N sequential running-stat updates
     reproduced exactly, deterministic fixed-order gradient reductions.
-  * eval mode under autograd (rare)   -> batched torch ops + the fused graph-filter kernels.
+  * eval mode with autograd enabled   -> NotImplementedError (no torch / cuDNN fallback on the product path).
 CUDA only: the module raises if asked to run on CPU tensors.
 """
 from __future__ import annotations
@@ -25,10 +25,9 @@ from typing import List
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as Fn
 
 from . import _lib
-from .graphml import GraphFilterBatch, graph_filter, NODE_MAJOR, _require_cuda
+from .graphml import GraphFilterBatch, _require_cuda
 
 _CONV_CH = [3, 32, 32, 64, 64, 128]
 _CONV_IDX = (0, 4, 7, 11, 14)
@@ -47,29 +46,6 @@ def weights_init(m):
     elif 'Linear' in name:
         nn.init.xavier_normal_(m.weight)
         m.bias.data.fill_(0.0)
-
-
-class _Conv3x3Fp32(torch.autograd.Function):
-    """3x3 / stride 1 / pad 1 convolution pinned to true fp32 in BOTH directions: cuDNN would
-    otherwise run fp32 convolutions on TF32 tensor cores (2e-4 relative error, measured), which
-    breaks the 1e-5 parity bar.  The flag is read when the kernels run, so the backward needs
-    its own guard -- hence a Function rather than a context manager around the forward."""
-
-    @staticmethod
-    def forward(ctx, x, w, b):
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            y = Fn.conv2d(x, w, b, stride=1, padding=1)
-        ctx.save_for_backward(x, w)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            gx, gw, gb = torch.ops.aten.convolution_backward(
-                gy.contiguous(), x, w, [w.shape[0]], [1, 1], [1, 1], [1, 1], False, [0, 0], 1,
-                [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]])
-        return gx, gw, gb
 
 
 class _PlannerTrainFn(torch.autograd.Function):
@@ -94,15 +70,19 @@ class _PlannerTrainFn(torch.autograd.Function):
         for l, ci in enumerate(_CONV_IDX):
             b = module.ConvLayers[ci + 1]
             if b.track_running_stats and b.running_mean is not None:
+                if b.momentum is None:
+                    raise NotImplementedError("gnn_pathplanning_b200: BatchNorm momentum=None (cumulative moving "
+                                              "average) is not supported by the native training path")
                 bn.running_mean[l] = b.running_mean.data_ptr()
                 bn.running_var[l] = b.running_var.data_ptr()
                 momentum = b.momentum
         ws = torch.empty(lib.gpp_planner_train_workspace_bytes(B, N, K) // 4 + 16, device=x.device, dtype=torch.float32)
         logits = torch.empty(N, B, 5, device=x.device, dtype=torch.float32)
-        stream = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.gpp_planner_train_forward(C.byref(w), C.byref(bn), momentum, x.data_ptr(), S3.data_ptr(),
-                                                 int(S3.dtype == torch.float64), logits.data_ptr(), ws.data_ptr(),
-                                                 B, N, K, stream))
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        with torch.cuda.device(x.device):
+            _lib.check(lib.gpp_planner_train_forward(C.byref(w), C.byref(bn), momentum, x.data_ptr(), S3.data_ptr(),
+                                                     int(S3.dtype == torch.float64), logits.data_ptr(), ws.data_ptr(),
+                                                     B, N, K, stream))
         with torch.no_grad():
             for ci in _CONV_IDX:
                 b = module.ConvLayers[ci + 1]
@@ -130,9 +110,11 @@ class _PlannerTrainFn(torch.autograd.Function):
         g.gf_w, g.gf_b = grads[22].data_ptr(), grads[23].data_ptr()
         g.action_w, g.action_b = grads[24].data_ptr(), grads[25].data_ptr()
         dl = dlogits.contiguous()
-        _lib.check(lib.gpp_planner_train_backward(C.byref(w), x.data_ptr(), S3.data_ptr(), int(S3.dtype == torch.float64),
-                                                  dl.data_ptr(), ws.data_ptr(), C.byref(g), B, N, module.K[0],
-                                                  torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x.device):
+            _lib.check(lib.gpp_planner_train_backward(C.byref(w), x.data_ptr(), S3.data_ptr(),
+                                                      int(S3.dtype == torch.float64), dl.data_ptr(), ws.data_ptr(),
+                                                      C.byref(g), B, N, module.K[0],
+                                                      torch.cuda.current_stream(x.device).cuda_stream))
         return (None, None, None) + tuple(grads)
 
 
@@ -145,8 +127,9 @@ def _fill_weights(params, module):
         w.conv_b[l] = params[5 + l].data_ptr()
         w.bn_w[l] = params[10 + l].data_ptr()
         w.bn_b[l] = params[15 + l].data_ptr()
-        w.bn_mean[l] = bnm.running_mean.data_ptr()
-        w.bn_var[l] = bnm.running_var.data_ptr()
+        if bnm.running_mean is not None:          # track_running_stats=False: train mode never reads them
+            w.bn_mean[l] = bnm.running_mean.data_ptr()
+            w.bn_var[l] = bnm.running_var.data_ptr()
     w.compress_w, w.compress_b = params[20].data_ptr(), params[21].data_ptr()
     w.gf_w, w.gf_b = params[22].data_ptr(), params[23].data_ptr()
     w.action_w, w.action_b = params[24].data_ptr(), params[25].data_ptr()
@@ -207,7 +190,21 @@ class DecentralPlannerNet(nn.Module):
         # native handles are per-process device resources: never pickled / deep-copied
         d = self.__dict__.copy()
         d["_native"] = {}
+        for k in ("_async_native", "_key_tensors", "_param_device"):
+            d.pop(k, None)
         return d
+
+    def load_state_dict(self, *a, **k):
+        self.__dict__["_key_tensors"] = None          # assign=True replaces the Parameter objects
+        return super().load_state_dict(*a, **k)
+
+    def refresh_weights(self) -> None:
+        """Forces the native weight arena to be re-staged on the next eval forward.  Needed only after writes
+        that bypass autograd's version counters (`p.data.copy_(...)`, `p.data.add_(...)`): optimizer steps,
+        `load_state_dict`, `.to()` and in-place ops on the parameters themselves are detected automatically."""
+        self.__dict__["_key_tensors"] = None
+        for nat in self._native.values():
+            nat.key = None
 
     # ------------------------------------------------------------------ API
     def addGSO(self, S):
@@ -229,7 +226,13 @@ class DecentralPlannerNet(nn.Module):
         elif not torch.is_grad_enabled():
             logits = self._forward_fused(inputTensor, S)           # [N,B,5]
         else:
-            logits = self._forward_autograd(inputTensor, S)        # eval-mode BN under autograd (rare)
+            # eval-mode BatchNorm under autograd: none of the reference's callers does this (test() runs under
+            # torch.no_grad(), agents/decentralplannerlocal.py:505; training calls model.train(), :283).  The native
+            # backward implements train-mode (batch-statistics) BatchNorm only, and there is deliberately no
+            # torch/cuDNN fallback on the product path.
+            raise NotImplementedError(
+                "gnn_pathplanning_b200: eval-mode forward with autograd enabled is not supported; wrap inference "
+                "in torch.no_grad() or switch the module to train() for a differentiable forward")
         return list(logits.unbind(0))
 
     def _train_params(self):
@@ -279,8 +282,9 @@ class DecentralPlannerNet(nn.Module):
                 if t.is_floating_point():
                     _require_cuda(t, "model parameter")
                     assert t.is_contiguous() and t.dtype == torch.float32
-            _lib.check(nat.lib.gpp_planner_set_weights(
-                nat.handle, C.byref(w), 1, torch.cuda.current_stream().cuda_stream))
+            with torch.cuda.device(idx):
+                _lib.check(nat.lib.gpp_planner_set_weights(
+                    nat.handle, C.byref(w), 1, torch.cuda.current_stream(idx).cuda_stream))
             nat.key = key
             nat.fresh = True
         mode = self.__dict__.get("_gf_mode", 0)
@@ -312,9 +316,10 @@ class DecentralPlannerNet(nn.Module):
             S3 = S3.float()
         S3 = S3.contiguous()
         logits = torch.empty(N, B, 5, device=x.device, dtype=torch.float32)
+        # the C entry point switches to the handle's device itself; the stream is the tensor's device's current one
         _lib.check(nat.lib.gpp_planner_forward(
             nat.handle, x.data_ptr(), S3.data_ptr(), int(S3.dtype == torch.float64),
-            logits.data_ptr(), None, B, N, torch.cuda.current_stream().cuda_stream))
+            logits.data_ptr(), None, B, N, torch.cuda.current_stream(x.device).cuda_stream))
         return logits
 
     def infer_host(self, x_host: torch.Tensor, S_host: torch.Tensor, out_host: torch.Tensor = None,
@@ -383,47 +388,3 @@ class DecentralPlannerNet(nn.Module):
     def wait(self, ticket: int) -> None:
         nat = self.__dict__["_async_native"]
         _lib.check(nat.lib.gpp_planner_wait(nat.handle, C.c_ulonglong(ticket)))
-
-    # ------------------------------------------------ autograd (training) path
-    def _bn_per_agent(self, h, bn, N):
-        """BatchNorm2d with the reference's per-agent semantics: the reference calls
-        ConvLayers once per agent (decentralplanner.py:284-286), so in train mode the batch
-        statistics are over (B,H,W) of ONE agent's slice and the running statistics are
-        updated N times per forward, in agent order.  h: [B*N, C, H, W] (b-major)."""
-        BN_, Cc, H, W = h.shape
-        B = BN_ // N
-        if not bn.training:
-            return Fn.batch_norm(h, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
-        hv = h.view(B, N * Cc, H, W)
-        out = Fn.batch_norm(hv, None, None, bn.weight.repeat(N), bn.bias.repeat(N), True, 0.0, bn.eps)
-        if bn.track_running_stats:
-            with torch.no_grad():
-                cnt = B * H * W
-                var, mean = torch.var_mean(h.detach().view(B, N, Cc, H * W), dim=(0, 3), unbiased=False)
-                var_unb = var * (cnt / max(cnt - 1, 1))
-                m = bn.momentum
-                # running <- (1-m) running + m stat_i, applied for i = 0..N-1 in order
-                wts = m * (1.0 - m) ** torch.arange(N - 1, -1, -1, device=h.device, dtype=torch.float32)
-                decay = (1.0 - m) ** N
-                bn.running_mean.mul_(decay).add_((wts[:, None] * mean).sum(0))
-                bn.running_var.mul_(decay).add_((wts[:, None] * var_unb).sum(0))
-                bn.num_batches_tracked += N
-        return out.view(BN_, Cc, H, W)
-
-    def _forward_autograd(self, x, S):
-        B, N = x.shape[0], x.shape[1]
-        h = x.reshape(B * N, 3, 11, 11).float()
-        for l, ci in enumerate(_CONV_IDX):
-            conv, bn = self.ConvLayers[ci], self.ConvLayers[ci + 1]
-            h = _Conv3x3Fp32.apply(h, conv.weight, conv.bias)
-            h = Fn.relu(self._bn_per_agent(h, bn, N))
-            if l % 2 == 0:
-                h = Fn.max_pool2d(h, 2)
-        lin = self.compressMLP[0]
-        feat = Fn.relu(Fn.linear(h.reshape(B * N, 128), lin.weight, lin.bias)).view(B, N, 128)
-        gf = self.GFL[0]
-        shared = graph_filter(feat, S, gf.weight, gf.bias, fuse_relu=True,
-                              x_layout=NODE_MAJOR, y_layout=NODE_MAJOR)        # [B,N,128]
-        act = self.actionsMLP[0]
-        logits = Fn.linear(shared, act.weight, act.bias)                       # [B,N,5]
-        return logits.permute(1, 0, 2)

@@ -193,35 +193,14 @@ int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const vo
 int gpp_planner_wait(gpp_planner* p, unsigned long long ticket);
 
 /* Which graph-filter kernel the planner uses: 0 = automatic (tensor cores once B*N >= 4096 node
- * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 3xTF32 kernel (gf_fwd_tc_kernel;
- * GPP_ERR_UNSUPPORTED at forward time if N/K do not fit its 128-row tile). */
+ * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 kernel (GPP_ERR_UNSUPPORTED at
+ * forward time if N/K do not fit its 128-row tile). */
 int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode);
 
 /* Which feature-extractor (CNN + compress MLP) kernel the planner uses: 0 = automatic (currently always the
  * CUDA-core kernel, the faster one at every measured size), 1 = CUDA-core fp32 kernel (feature_kernel),
  * 2 = tcgen05 3xTF32 implicit-GEMM kernel (feature_tc_kernel). */
 int gpp_planner_set_feature_mode(gpp_planner* p, int mode);
-
-/* Test hook for the tcgen05 plumbing: D[128][128] = A[128][32] . B[128][32]^T on the tensor cores
- * (A, B tf32-representable fp32, row-major, device memory). */
-int gpp_debug_umma_selftest(const float* A, const float* B, float* D, void* stream);
-
-/* Debug: per-phase cycle totals of the tcgen05 filter kernel (filled only when the environment variable
- * GPP_TC_TIMING is set): staging loop, wait for the last MMA, TMEM read-out, propagation, stores, tiles. */
-int gpp_debug_tc_timing(unsigned long long* out6);
-/* Same for block 0 of the CUDA-core filter kernel (environment variable GPP_GF_TIMING): prologue, x/S staging,
- * propagation, tap contraction, epilogue, action MLP + column-half merge. */
-int gpp_debug_gf_timing(unsigned long long* out6);
-/* Same for the tcgen05 feature extractor: [3*L + {0,1,2}] = layer L staging loop / wait for MMAs / epilogue,
- * [18] = agent tiles (thread 0 of every CTA). */
-int gpp_debug_feature_tc_timing(unsigned long long* out20);
-/* Block 0 of the CUDA-core feature extractor (environment variable GPP_FE_TIMING): input staging, conv0, conv1,
- * conv2, conv3, conv4, compress MLP + store. */
-int gpp_debug_feature_timing(unsigned long long* out7);
-/* Single kernels of the native training path (profiles/debug_train_ops.py): op 0 conv3x3 forward (a = input, b = filters,
- * c = bias), op 1 conv3x3 input gradient (a = dz, b = filters), op 2 max-pool gradient (a = activation, b = pooled grad). */
-int gpp_debug_train_kernel(int op, const float* a, const float* b, const float* c, float* out, int M, int Cin, int Cout,
-                           int H, void* stream);
 
 /* Per-kernel device timing for the roofline report: when enabled, gpp_planner_forward records
  * CUDA events before / between / after its two kernels on the launching stream (at most 8192

@@ -71,7 +71,9 @@ def batch_lsigf(h: torch.Tensor, S: torch.Tensor, x: torch.Tensor,
     taps = [cur.reshape(B, 1, 1, G, N).repeat(1, E, 1, 1, 1)]           # k = 0 (:2345)
     z = taps[0]
     for _k in range(1, K):
-        cur = torch.matmul(cur, Sb.float())                              # :2350
+        # :2350 `S.float()`; when the oracle is evaluated in float64 (x float64: the ground truth the f32
+        # implementations are measured against) the GSO keeps full precision instead
+        cur = torch.matmul(cur, Sb.float() if cur.dtype == torch.float32 else Sb.to(cur.dtype))
         z = torch.cat((z, cur.reshape(B, E, 1, G, N)), dim=2)            # :2351-2352
     rows = z.permute(0, 4, 1, 2, 3).reshape(B, N, E * K * G)             # :2361
     y = torch.matmul(rows, h.reshape(F_out, E * K * G).t()).permute(0, 2, 1)   # :2361-2362
@@ -121,7 +123,8 @@ def graph_filter_f64(weight, bias, S, x) -> np.ndarray:
 # Whole planner forward
 # ----------------------------------------------------------------------------
 def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool,
-                   bn_state: Optional[Dict[str, torch.Tensor]], stats: Optional[dict] = None) -> torch.Tensor:
+                   bn_state: Optional[Dict[str, torch.Tensor]], stats: Optional[dict] = None,
+                   agent: int = 0, relu_force: Optional[dict] = None) -> torch.Tensor:
     """ConvLayers applied to ONE agent's [B,3,11,11] slice (decentralplanner.py:286):
     5 x (Conv3x3 s1 p1 + BatchNorm2d + ReLU), MaxPool2d(2) after conv 0, 2, 4."""
     h = xi
@@ -145,7 +148,24 @@ def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool
                 m = float(h.abs().min() / h.abs().max().clamp_min(1e-30))
             stats.setdefault("relu_margin", [1.0] * 5)
             stats["relu_margin"][l] = min(stats["relu_margin"][l], m)
-        h = Fn.relu(h)
+            tau = stats.get("kink_tau")
+            if tau:
+                # every pre-activation closer to the kink than tau x (layer scale): (agent, layer, flat index, value)
+                with torch.no_grad():
+                    flat = h.reshape(-1)
+                    near = torch.nonzero(flat.abs() < tau * h.abs().max()).reshape(-1)
+                    for idx in near.tolist():
+                        stats.setdefault("near_kink", []).append((agent, l, idx, float(flat[idx])))
+        forced = relu_force.get((agent, l)) if relu_force else None
+        if forced:
+            # ReLU with chosen on/off states for the listed elements (kink-flip analysis in the tests)
+            mask = (h > 0).to(h.dtype)
+            mflat = mask.reshape(-1)
+            for idx, on in forced:
+                mflat[idx] = 1.0 if on else 0.0
+            h = h * mask
+        else:
+            h = Fn.relu(h)
         if l % 2 == 0:
             h = Fn.max_pool2d(h, kernel_size=2)
     return h
@@ -154,20 +174,22 @@ def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool
 def planner_forward(sd: Dict[str, torch.Tensor], S: torch.Tensor, x: torch.Tensor,
                     training: bool = False,
                     bn_state: Optional[Dict[str, torch.Tensor]] = None,
-                    stats: Optional[dict] = None) -> List[torch.Tensor]:
+                    stats: Optional[dict] = None, relu_force: Optional[dict] = None) -> List[torch.Tensor]:
     """Restates DecentralPlannerNet.addGSO + forward (decentralplanner.py:266-318).
 
     sd: state_dict-keyed tensors; S [B,N,N]; x [B,N,3,11,11] f32.
     Returns the reference's Python list of N tensors [B,5] (raw logits).
     `training=True` uses batch statistics per agent call and updates `bn_state`
     (running_mean / running_var / num_batches_tracked clones) in agent order.
+    Passing float64 `sd` / `x` evaluates the same op sequence in double precision (ground truth for
+    the tests); `stats` / `relu_force` serve the ReLU-kink analysis of the gradient tests.
     """
     assert S.dim() == 3                                                  # :271
     S4 = S.unsqueeze(1)                                                  # :272
     B, N = x.shape[0], x.shape[1]
-    feat = torch.zeros(B, NUM_FEATURES, N)                               # :283
+    feat = torch.zeros(B, NUM_FEATURES, N, dtype=x.dtype)                # :283 (float32 in the reference)
     for i in range(N):                                                   # :284
-        fm = _cnn_one_agent(sd, x[:, i], training, bn_state, stats)      # :285-286
+        fm = _cnn_one_agent(sd, x[:, i], training, bn_state, stats, i, relu_force)   # :285-286
         flat = fm.reshape(fm.shape[0], -1)                               # :287
         comp = Fn.relu(Fn.linear(flat, sd["compressMLP.0.weight"], sd["compressMLP.0.bias"]))  # :289
         feat[:, :, i] = comp                                             # :290

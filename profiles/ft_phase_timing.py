@@ -1,5 +1,4 @@
 import os, sys, ctypes as C
-os.environ["GPP_TC_TIMING"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gnn_pathplanning_b200 as gp
@@ -14,7 +13,7 @@ m = gp.DecentralPlannerNet(Cfg()); m.load_state_dict(sd); m = m.cuda().eval(); m
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 x, S = synthetic.make_batch(64, 10, 20, seed=3)
 xt = torch.from_numpy(x).repeat(B // 64, 1, 1, 1, 1).cuda(); St = torch.from_numpy(S).repeat(B // 64, 1, 1).cuda()
-lib = _lib.load(); out = (C.c_ulonglong * 32)()
+_lib.set_debug_option("tc_timing", 1); lib = _lib.load(); out = (C.c_ulonglong * 32)()
 with torch.no_grad():
     for _ in range(3):
         m.addGSO(St); m(xt)

@@ -14,6 +14,8 @@ import sys, json, torch
 sys.path.insert(0, %r)
 import gnn_pathplanning_b200 as gp
 N, K = int(sys.argv[1]), int(sys.argv[2])
+from gnn_pathplanning_b200 import _lib
+_lib.set_debug_option("gf_mode", int(sys.argv[3]))
 torch.manual_seed(0)
 w = ((torch.rand(128, 1, K, 128) - 0.5) * 0.2).cuda()
 b = (torch.rand(128, 1) - 0.5).cuda()
@@ -46,8 +48,7 @@ if __name__ == "__main__":
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     for mode, name in ((1, "cuda-core"), (2, "tcgen05")):
-        env = dict(os.environ, GPP_GF_MODE=str(mode))
-        r = subprocess.run([sys.executable, "-c", CHILD % ROOT, str(N), str(K)], env=env, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, "-c", CHILD % ROOT, str(N), str(K), str(mode)], capture_output=True, text=True)
         if r.returncode != 0:
             print(name, "FAILED", r.stderr[-400:])
             continue

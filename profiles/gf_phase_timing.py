@@ -1,8 +1,6 @@
 """Per-phase cycles of block 0 of feature_kernel and gf_fwd_kernel inside the planner forward
-(GPP_FE_TIMING / GPP_GF_TIMING hooks)."""
+("fe_timing" / "gf_timing" debug options)."""
 import os, sys, ctypes as C
-os.environ["GPP_GF_TIMING"] = "1"
-os.environ["GPP_FE_TIMING"] = "1"
 sys.path.insert(0, "/root/repo")
 import torch
 import gnn_pathplanning_b200 as gp
@@ -14,6 +12,8 @@ class Cfg:
 
 names = ["prologue", "stage x/S", "propagate", "contract", "epilogue", "action+merge"]
 lib = _lib.load()
+_lib.set_debug_option("gf_timing", 1)
+_lib.set_debug_option("fe_timing", 1)
 for (B, N) in [(64, 10), (256, 10), (1024, 10), (64, 20)]:
     m = gp.DecentralPlannerNet(Cfg(N, 3)).cuda().eval()
     m.set_graph_filter_mode("cuda")

@@ -1,5 +1,4 @@
 import os, sys, ctypes as C
-os.environ["GPP_GF_MODE"]="2"; os.environ["GPP_TC_TIMING"]="1"
 sys.path.insert(0,"/root/repo")
 import torch, gnn_pathplanning_b200 as gp
 from gnn_pathplanning_b200 import _lib
@@ -7,6 +6,7 @@ B,N,K=32768,10,3
 w=((torch.rand(128,1,K,128)-0.5)*0.2).cuda(); b=(torch.rand(128,1)-0.5).cuda()
 x=torch.randn(B,N,128,device="cuda"); S=torch.rand(B,N,N,device="cuda")*0.2
 lib=_lib.load()
+_lib.set_debug_option("gf_mode", 2); _lib.set_debug_option("tc_timing", 1)
 for i in range(3): y=gp.graph_filter(x,S,w,b,True,gp.NODE_MAJOR,gp.NODE_MAJOR)
 out=(C.c_ulonglong*6)()
 lib.gpp_debug_tc_timing(out)

@@ -125,9 +125,12 @@ def test_zero_padding_path_and_asserts():
 
 
 def test_properties_at_full_size():
-    """BASELINE config 4 size (N=40, B=256): linearity in x, K=1 reduces to a per-node linear map,
-    identity GSO collapses the taps, permutation equivariance."""
+    """BASELINE config 4 size (N=40, B=256 -> 10,240 node rows): the CPU oracle at the full size in both
+    layouts (feature-major = the reference API, CUDA-core kernel; node-major = the planner-internal layout, which
+    the automatic choice routes to the tcgen05 kernel at this size), then size-independent properties: linearity
+    in x, K=1 reduces to a per-node linear map, identity GSO collapses the taps, permutation equivariance."""
     import gnn_pathplanning_b200 as g
+    from oracle import planner_oracle as po
     gen = torch.Generator().manual_seed(99)
     B, N, K = 256, 40, 3
     w = ((torch.rand(128, 1, K, 128, generator=gen) - 0.5) * 0.2).cuda()
@@ -136,6 +139,10 @@ def test_properties_at_full_size():
     x1 = torch.randn(B, 128, N, generator=gen).cuda()
     x2 = torch.randn(B, 128, N, generator=gen).cuda()
     f = lambda x, bias=None, SS=S, ww=w: g.graph_filter(x, SS, ww, bias)
+    ref = po.batch_lsigf(w.cpu(), S.cpu().unsqueeze(1), x1.cpu(), b.cpu()).numpy()
+    assert rel_err(f(x1, b).cpu().numpy(), ref) <= TOL
+    y_nm = g.graph_filter(x1.permute(0, 2, 1).contiguous(), S, w, b, False, g.NODE_MAJOR, g.NODE_MAJOR)
+    assert rel_err(y_nm.permute(0, 2, 1).cpu().numpy(), ref) <= TOL
     ya, yb, yab = f(x1), f(x2), f(2.0 * x1 - 3.0 * x2)
     assert rel_err(yab.cpu().numpy(), (2.0 * ya - 3.0 * yb).cpu().numpy()) <= TOL
     eye = torch.eye(N, device="cuda").expand(B, N, N).contiguous()

@@ -161,10 +161,48 @@ def test_async_host_calls_match_sync(golden):
         m.infer_host_async(torch.from_numpy(g["x"].astype(np.float32)), S, outs[0])     # pageable memory
 
 
-@pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (20, 3, 16, 28)])
-def test_train_step_vs_oracle_at_config_sizes(N, K, B, map_w):
-    """BASELINE configs 3 / 5 (per-GPU shard): one training forward/backward against the CPU oracle's
-    autograd -- logits, loss, every gradient, BatchNorm running statistics."""
+def _oracle_train_step(sd, St, xt, tgt, dtype, relu_force=None, stats=None):
+    """One train-mode forward + loss + backward of the oracle in `dtype`; returns (logits, loss, grads, bn_state)."""
+    from oracle import planner_oracle as po
+    cast = (lambda v: v.clone().to(dtype)) if dtype != torch.float32 else (lambda v: v.clone())
+    bn = {k: (cast(v) if v.is_floating_point() else v.clone()) for k, v in sd.items() if "running" in k or "tracked" in k}
+    leaf = {k: (cast(v).requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v)
+            for k, v in sd.items()}
+    out = po.planner_forward(leaf, St.to(dtype), xt.to(dtype), True, bn, stats, relu_force)
+    loss = po.planner_loss(out, tgt)
+    loss.backward()
+    grads = {k: v.grad.double().numpy() for k, v in leaf.items() if torch.is_tensor(v) and v.requires_grad}
+    return torch.stack(out).detach().double().numpy(), float(loss), grads, bn
+
+
+_CONV_BIAS = tuple("ConvLayers.%d.bias" % ci for ci in (0, 4, 7, 11, 14))
+
+
+def _grad_err(got, ref):
+    """Worst per-tensor max|d|/max|ref| over all parameters.  Conv biases feed a train-mode BatchNorm: their
+    true gradient is 0 and every implementation holds rounding noise there -> absolute scale."""
+    worst, where = 0.0, None
+    for n_, r in ref.items():
+        e = float(np.abs(got[n_] - r).max()) if n_ in _CONV_BIAS else rel_err(got[n_], r)
+        if e > worst:
+            worst, where = e, n_
+    return worst, where
+
+
+@pytest.mark.parametrize("N,K,B,map_w", [(10, 3, 64, 20), (20, 3, 64, 28)])
+def test_train_step_vs_fp64_oracle_at_config_sizes(N, K, B, map_w):
+    """BASELINE configs 3 / 5 (C5 = 64 episodes x 20 agents per GPU shard): one training forward/backward.
+
+    Forward (logits, loss, BatchNorm running statistics): against the fp32 oracle at the 1e-5 bar.
+    Gradients: pinned to a FLOAT64 evaluation of the oracle, the ground truth both fp32 implementations
+    approximate.  Two correct fp32 implementations may resolve a pre-activation that sits within rounding
+    distance of the ReLU kink differently; instead of widening the tolerance the test lists every pre-activation
+    within 1e-6 x (layer scale) of zero in the fp64 run, evaluates the fp64 gradients for the natural mask and
+    for single / double flips of exactly those elements, and requires the CUDA gradients to match ONE of those
+    ground truths -- to within 1e-5, or, where fp32 round-off itself is larger than that, to within 1.5x the
+    distance of the reference-order fp32 oracle from its own best-matching ground truth.  Flips are counted and
+    printed."""
+    import itertools
     from gnn_pathplanning_b200 import synthetic
     from oracle import planner_oracle as po
     sd = po.init_state_dict(K, seed=11)
@@ -172,54 +210,73 @@ def test_train_step_vs_oracle_at_config_sizes(N, K, B, map_w):
     tgt = torch.from_numpy(synthetic.random_targets(B, N, seed=5))
     x, S = synthetic.make_batch(B, N, map_w, seed=21)
     xt, St = torch.from_numpy(x), torch.from_numpy(S)
-    bn = {k: v.clone() for k, v in sd.items() if "running" in k or "tracked" in k}
-    leaf = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v)
-            for k, v in sd.items()}
-    ref_out = po.planner_forward(leaf, St, xt, True, bn)
-    ref_loss = po.planner_loss(ref_out, tgt)
-    ref_loss.backward()
+    ref_logits, ref_loss, g32, bn32 = _oracle_train_step(sd, St, xt, tgt, torch.float32)
     m = _model(sd, N, K).train()
     m.addGSO(St.cuda())
     out = m(xt.cuda())
     loss = po.planner_loss(out, tgt.cuda())
     loss.backward()
-    assert rel_err(torch.stack(out).detach().cpu().numpy(), torch.stack(ref_out).detach().numpy()) <= TOL
-    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * max(1.0, abs(ref_loss.item()))
-    # Gradient comparison, ReLU-kink aware.  With ~10^5..10^6 activations per layer some pre-activation always
-    # sits within ~1e-7 of zero (relative), closer than the ~1e-6 by which two correct fp32 convolutions differ, so
-    # one implementation may switch that element on and the other off.  Such a flip changes the gradients of ITS
-    # BatchNorm channel at that layer and, through it, everything upstream -- while every other channel of the layer
-    # still matches to ~1e-8 (observed: one element of 164k, channel 28 of layer 3).  The check therefore walks from
-    # the output towards the input: strict (5e-5) until a layer shows a mismatch confined to <= 2 channels, which is
-    # accepted as kink flips; layers upstream of it are then only required to agree within 2e-2.
-    grads = {n_: p.grad.cpu().numpy() for n_, p in m.named_parameters()}
-    refs = {n_: leaf[n_].grad.numpy() for n_ in grads}
-    for n_ in ("actionsMLP.0.weight", "actionsMLP.0.bias", "GFL.0.weight", "GFL.0.bias",
-               "compressMLP.0.weight", "compressMLP.0.bias"):
-        assert rel_err(grads[n_], refs[n_]) <= 5e-5, n_
-    strict = True
-    for ci in (14, 11, 7, 4, 0):
-        wn, gn, bnn = "ConvLayers.%d.weight" % ci, "ConvLayers.%d.weight" % (ci + 1), "ConvLayers.%d.bias" % (ci + 1)
-        if strict:
-            scale = max(np.abs(refs[bnn]).max(), 1e-30)
-            bad = np.nonzero(np.abs(grads[bnn] - refs[bnn]) > 5e-5 * scale)[0]
-            if len(bad) == 0:
-                assert rel_err(grads[wn], refs[wn]) <= 5e-5 and rel_err(grads[gn], refs[gn]) <= 5e-5, ci
-                continue
-            assert len(bad) <= 2, "layer %d: %d BatchNorm channels differ -- not a ReLU-kink flip" % (ci, len(bad))
-            good = np.setdiff1d(np.arange(refs[bnn].shape[0]), bad)
-            wscale = max(np.abs(refs[wn]).max(), 1e-30)
-            assert np.abs(grads[wn][good] - refs[wn][good]).max() <= 5e-5 * wscale, ci     # other channels exact
-            print("ReLU-kink flip accepted at ConvLayers.%d, channels %s" % (ci, bad.tolist()))
-            strict = False
-        for n_ in (wn, gn, bnn):
-            assert rel_err(grads[n_], refs[n_]) <= 2e-2, n_
-    for ci in (0, 4, 7, 11, 14):      # conv biases: true gradient is 0 (a train-mode BatchNorm follows)
-        n_ = "ConvLayers.%d.bias" % ci
-        assert np.abs(grads[n_] - refs[n_]).max() <= 1e-5, n_
+    assert rel_err(torch.stack(out).detach().cpu().numpy(), ref_logits) <= TOL
+    assert abs(loss.item() - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
     after = m.state_dict()
-    for k, v in bn.items():
+    for k, v in bn32.items():
         assert rel_err(after[k].double().cpu().numpy(), v.double().numpy()) <= TOL, k
+    gc = {n_: p.grad.double().cpu().numpy() for n_, p in m.named_parameters()}
+
+    stats = {"kink_tau": 1e-6}
+    truths = {(): _oracle_train_step(sd, St, xt, tgt, torch.float64, None, stats)[2]}
+    near = stats.get("near_kink", [])
+    assert len(near) <= 12, "too many pre-activations at the ReLU kink for the flip analysis: %d" % len(near)
+
+    def truth(flips):
+        if flips not in truths:
+            force = {}
+            for (agent, layer, idx, val) in flips:
+                force.setdefault((agent, layer), []).append((idx, not (val > 0)))
+            truths[flips] = _oracle_train_step(sd, St, xt, tgt, torch.float64, force)[2]
+        return truths[flips]
+
+    def best(got):
+        cands = [()] + [(e,) for e in near] + list(itertools.combinations(near, 2))
+        top = (float("inf"), None, None)
+        for c in cands:
+            e, where = _grad_err(got, truth(c))
+            if e < top[0]:
+                top = (e, where, c)
+            if e <= 1e-5:
+                break
+        return top
+
+    e_cuda, where_cuda, flips_cuda = best(gc)
+    e_ref, where_ref, flips_ref = best(g32)
+    print("gradients vs fp64 truth: CUDA %.2e (%s, %d kink flips), reference-order fp32 oracle %.2e (%s, %d flips); "
+          "%d pre-activations within 1e-6 of the kink" % (e_cuda, where_cuda, len(flips_cuda), e_ref, where_ref,
+                                                         len(flips_ref), len(near)))
+    assert e_cuda <= max(1e-5, 1.5 * e_ref), (e_cuda, where_cuda, e_ref)
+
+
+def test_full_c4_eval_vs_oracle():
+    """BASELINE config 4 at FULL size: K=3, 40 agents, 50x50 map, batch 256 (10,240 node rows: the automatic
+    choice routes the graph filter to the tcgen05 kernel); the forced tcgen05 and CUDA-core filters as well."""
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    N, K, B, map_w = 40, 3, 256, 50
+    sd = po.init_state_dict(K, seed=41)
+    po.randomize_bn_stats(sd, seed=42)
+    x, S = synthetic.make_batch(B, N, map_w, seed=43)
+    xt, St = torch.from_numpy(x), torch.from_numpy(S)
+    with torch.no_grad():
+        ref = torch.stack(po.planner_forward(sd, St, xt)).numpy()
+    m = _model(sd, N, K).eval()
+    top2 = np.sort(ref, -1)
+    clear = (top2[..., -1] - top2[..., -2]) > 1e-4 * np.abs(ref).max()
+    for mode in ("auto", "tc", "cuda"):
+        m.set_graph_filter_mode(mode)
+        with torch.no_grad():
+            m.addGSO(St.cuda())
+            got = torch.stack(m(xt.cuda())).cpu().numpy()
+        assert rel_err(got, ref) <= TOL, mode
+        assert np.array_equal(got.argmax(-1)[clear], ref.argmax(-1)[clear]), mode
 
 
 def test_optimizer_steps_follow_oracle():

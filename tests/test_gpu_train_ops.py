@@ -19,8 +19,6 @@ def _rel(a, b):
 def test_conv_and_pool_kernels(M, Cin, Cout, H):
     from gnn_pathplanning_b200 import _lib
     lib = _lib.load()
-    lib.gpp_debug_train_kernel.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p]
-    lib.gpp_debug_train_kernel.restype = C.c_int
     st = torch.cuda.current_stream().cuda_stream
     g = torch.Generator(device="cuda").manual_seed(M * 131 + H)
     x = torch.randn(M, Cin, H, H, device="cuda", generator=g)
@@ -47,3 +45,12 @@ def test_conv_and_pool_kernels(M, Cin, Cout, H):
         assert lib.gpp_debug_train_kernel(2, a.data_ptr(), dp.contiguous().data_ptr(), None, da.data_ptr(), M, Cin, Cout,
                                           H, st) == 0
         assert torch.equal(da, a.grad)       # ties (zeros after the ReLU) go to the first maximum, as in torch
+    # weight + bias gradient (per-chunk partial sums + fixed-order chunk reduction, as the training step runs it)
+    out = torch.empty(Cout * Cin * 9 + Cout, device="cuda")
+    assert lib.gpp_debug_train_kernel(3, dz.data_ptr(), x.data_ptr(), None, out.data_ptr(), M, Cin, Cout, H, st) == 0
+    xd = x.double().requires_grad_(False)
+    wd = w.double().clone().requires_grad_(True)
+    bd = b.double().clone().requires_grad_(True)
+    (Fn.conv2d(xd, wd, bd, padding=1) * dz.double()).sum().backward()
+    assert _rel(out[:Cout * Cin * 9].view(Cout, Cin, 3, 3), wd.grad) <= TOL
+    assert _rel(out[Cout * Cin * 9:], bd.grad) <= TOL
