@@ -882,7 +882,16 @@ int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const floa
                          float* y, const float* wa, const float* ba, float* logits, int B, int N, int K,
                          int relu, int allow_bulk, cudaStream_t st);
 
-// debug override for the standalone op (gpp_debug_set_option("gf_mode", m)): 0 auto, 1 CUDA-core, 2 tcgen05
+// CTA-pair fp16-split tcgen05 kernel (graph_filter_pair.cu)
+size_t gf_pair_image_bytes(int K);
+bool gf_pair_supported(int N, int K);
+int launch_prep_pair_taps(const float* w, void* img, int K, cudaStream_t st);
+int launch_gf_forward_pair(const float* x, const void* S, int s_is_f64, const void* wimg, const float* bias, float* y,
+                           const float* wa_host, const float* ba_host, float* logits, int B, int N, int K, int relu,
+                           cudaStream_t st);
+
+// debug override for the standalone op (gpp_debug_set_option("gf_mode", m)): 0 auto, 1 CUDA-core, 2 tcgen05 3xTF32,
+// 3 tcgen05 CTA-pair fp16-split
 static int standalone_gf_mode() { return debug_option(DBG_GF_MODE); }
 }  // namespace gpp
 
@@ -890,7 +899,10 @@ using namespace gpp;
 
 extern "C" size_t gpp_graph_filter_workspace_bytes(int G, int F, int K) {
     // k-major transposed taps (CUDA-core kernel) or split/swizzled chunk images (tensor-core kernel)
-    if (G == GF_C && F == GF_C) return sizeof(float) * gf_tc_image_floats(K);
+    if (G == GF_C && F == GF_C) {
+        const size_t tc = sizeof(float) * gf_tc_image_floats(K), pair = gf_pair_image_bytes(K);
+        return tc > pair ? tc : pair;
+    }
     return 0;
 }
 
@@ -909,6 +921,14 @@ extern "C" int gpp_graph_filter_forward(const float* x, const void* S, int s_is_
         GPP_REQUIRE(workspace && aligned16(workspace), GPP_ERR_INVALID,
                     "graph_filter_forward: a 16-byte aligned workspace is required");
         const int mode = standalone_gf_mode();
+        const bool node_major = x_layout == GPP_NODE_MAJOR && y_layout == GPP_NODE_MAJOR;
+        GPP_REQUIRE(mode != 3 || (node_major && gf_pair_supported(N, K)), GPP_ERR_UNSUPPORTED,
+                    "graph_filter_forward: the CTA-pair kernel needs node-major layouts and a supported N / K (N=%d K=%d)", N, K);
+        if (node_major && gf_pair_supported(N, K) && (mode == 3 || (mode == 0 && (size_t)B * N >= 4096))) {
+            int rc = launch_prep_pair_taps(w, workspace, K, st);
+            if (rc) return rc;
+            return launch_gf_forward_pair(x, S, s_is_f64, workspace, bias, y, nullptr, nullptr, nullptr, B, N, K, fuse_relu, st);
+        }
         if (x_layout == GPP_NODE_MAJOR && y_layout == GPP_NODE_MAJOR && mode != 1 && gf_tc_tile_samples(N, K) > 0 &&
             (mode == 2 || (size_t)B * N >= 4096)) {
             float* img = reinterpret_cast<float*>(workspace);

@@ -57,6 +57,14 @@ int launch_gf_forward_tc(const float* x, const void* S, int s_is_f64, const floa
                          float* y, const float* wa, const float* ba, float* logits, int B, int N, int K,
                          int relu, int allow_bulk, cudaStream_t st);
 
+// CTA-pair fp16-split tcgen05 path (graph_filter_pair.cu)
+size_t gf_pair_image_bytes(int K);
+bool gf_pair_supported(int N, int K);
+int launch_prep_pair_taps(const float* w, void* img, int K, cudaStream_t st);
+int launch_gf_forward_pair(const float* x, const void* S, int s_is_f64, const void* wimg, const float* bias, float* y,
+                           const float* wa_host, const float* ba_host, float* logits, int B, int N, int K, int relu,
+                           cudaStream_t st);
+
 // Host -> device staging as a kernel: a few CTAs pull pinned (device-mapped) host memory over PCIe with
 // 16-byte loads and store it to HBM.  Runs on the copy stream next to the compute kernels of the previous
 // step (they leave SMs free at rollout batch sizes); n16 = number of 16-byte units, tail bytes separately.
@@ -120,10 +128,11 @@ struct gpp_planner {
     float* arena;        // prepared weights
     size_t off_w[6];     // conv0..4 k-major, compress k-major
     size_t off_sc[5], off_sh[5];
-    size_t off_b5, off_gfw, off_gfws, off_gfb, off_wa, off_ba, off_gfimg, arena_floats;
+    size_t off_b5, off_gfw, off_gfws, off_gfb, off_wa, off_ba, off_gfimg, off_gfpair, arena_floats;
+    float wa_host[5 * 128 + 8];   // host copy of the action MLP: the CTA-pair filter kernel takes it as kernel parameters
     bool pdl_ok;         // the kernels before the next forward in its stream only wrote what it reads after its
                          // griddepcontrol.wait (false right after the weights were re-staged)
-    int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
+    int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 3xTF32 kernel, 3 tcgen05 CTA-pair fp16-split kernel
     int fe_mode;         // feature extractor: 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
     size_t off_fimg[6];  // tcgen05 filter chunk images of conv0..4 and the compress MLP
     bool weights_set;
@@ -199,6 +208,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     p->off_wa = take(5 * 128);
     p->off_ba = take(64);
     p->off_gfimg = take(gf_tc_image_floats(K));      // pre-split, pre-swizzled tcgen05 B-operand chunks
+    p->off_gfpair = take(K <= 3 ? gf_pair_image_bytes(K) / 4 + 16 : 16);
     for (int l = 0; l < 6; ++l) p->off_fimg[l] = take(feature_tc_image_floats(l));
     p->arena_floats = off;
     if (cudaMalloc(&p->arena, sizeof(float) * off) != cudaSuccess) {
@@ -243,7 +253,7 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
 }
 
 extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
-    GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_graph_filter_mode: mode must be 0, 1 or 2");
+    GPP_REQUIRE(p && mode >= 0 && mode <= 3, GPP_ERR_INVALID, "planner_set_graph_filter_mode: mode must be 0, 1, 2 or 3");
     p->gf_mode = mode;
     return GPP_OK;
 }
@@ -401,11 +411,24 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     if (rc) return rc;
     rc = launch_prep_umma_taps(d.gf_w, A + p->off_gfimg, K, st);
     if (rc) return rc;
+    if (K <= 3) {
+        rc = launch_prep_pair_taps(d.gf_w, A + p->off_gfpair, K, st);
+        if (rc) return rc;
+    }
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_b5, d.compress_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_gfb, d.gf_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_wa, d.action_w, sizeof(float) * 5 * 128, cudaMemcpyDeviceToDevice, st));
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_ba, d.action_b, sizeof(float) * 5, cudaMemcpyDeviceToDevice, st));
-    if (!on_device) GPP_CUDA_OK(cudaStreamSynchronize(st));
+    // host copy of the 5 x 128 action MLP (kernel parameters of the CTA-pair filter kernel); weights change rarely
+    if (on_device) {
+        GPP_CUDA_OK(cudaMemcpyAsync(p->wa_host, d.action_w, sizeof(float) * 5 * 128, cudaMemcpyDeviceToHost, st));
+        GPP_CUDA_OK(cudaMemcpyAsync(p->wa_host + 640, d.action_b, sizeof(float) * 5, cudaMemcpyDeviceToHost, st));
+        GPP_CUDA_OK(cudaStreamSynchronize(st));
+    } else {
+        memcpy(p->wa_host, w->action_w, sizeof(float) * 5 * 128);
+        memcpy(p->wa_host + 640, w->action_b, sizeof(float) * 5);
+        GPP_CUDA_OK(cudaStreamSynchronize(st));
+    }
     p->weights_set = true;
     return GPP_OK;
 }
@@ -483,8 +506,15 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     const bool tc_fits = gf_tc_tile_samples(N, p->K) > 0;
     GPP_REQUIRE(p->gf_mode != 2 || tc_fits, GPP_ERR_UNSUPPORTED,
                 "planner_forward: tensor-core graph filter requested but N=%d K=%d does not fit its tile", N, p->K);
-    const bool use_tc = tc_fits && (p->gf_mode == 2 || (p->gf_mode == 0 && rows >= 4096));
-    if (use_tc)
+    const bool pair_fits = gf_pair_supported(N, p->K);
+    GPP_REQUIRE(p->gf_mode != 3 || pair_fits, GPP_ERR_UNSUPPORTED,
+                "planner_forward: CTA-pair graph filter requested but N=%d K=%d is outside its envelope", N, p->K);
+    const bool use_pair = pair_fits && (p->gf_mode == 3 || (p->gf_mode == 0 && rows >= 4096));
+    const bool use_tc = !use_pair && tc_fits && (p->gf_mode == 2 || (p->gf_mode == 0 && rows >= 4096));
+    if (use_pair)
+        rc = launch_gf_forward_pair(feat, S, s_is_f64, A + p->off_gfpair, A + p->off_gfb, nullptr, p->wa_host,
+                                    p->wa_host + 640, logits, B, N, p->K, 1, st);
+    else if (use_tc)
         rc = launch_gf_forward_tc(feat, S, s_is_f64, A + p->off_gfimg, A + p->off_gfb, nullptr, A + p->off_wa,
                                   A + p->off_ba, logits, B, N, p->K, 1, allow_bulk, st);
     else {

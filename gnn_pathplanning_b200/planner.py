@@ -298,8 +298,9 @@ class DecentralPlannerNet(nn.Module):
         return nat
 
     def set_graph_filter_mode(self, mode: str) -> None:
-        """'auto' (default), 'cuda' (fp32 CUDA-core kernel) or 'tc' (tcgen05 3xTF32 kernel)."""
-        self.__dict__["_gf_mode"] = {"auto": 0, "cuda": 1, "tc": 2}[mode]
+        """'auto' (default), 'cuda' (fp32 CUDA-core kernel), 'tc' (tcgen05 3xTF32 kernel) or 'pair' (tcgen05
+        CTA-pair fp16-split kernel)."""
+        self.__dict__["_gf_mode"] = {"auto": 0, "cuda": 1, "tc": 2, "pair": 3}[mode]
 
     def set_feature_mode(self, mode: str) -> None:
         """Feature extractor kernel: 'auto' (default), 'cuda' (fp32 CUDA cores) or 'tc' (tcgen05 3xTF32)."""

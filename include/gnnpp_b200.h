@@ -193,8 +193,9 @@ int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const vo
 int gpp_planner_wait(gpp_planner* p, unsigned long long ticket);
 
 /* Which graph-filter kernel the planner uses: 0 = automatic (tensor cores once B*N >= 4096 node
- * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 kernel (GPP_ERR_UNSUPPORTED at
- * forward time if N/K do not fit its 128-row tile). */
+ * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 3xTF32 kernel (gf_fwd_tc_kernel),
+ * 3 = tcgen05 CTA-pair fp16-split kernel (gf_fwd_pair_kernel).  GPP_ERR_UNSUPPORTED at forward
+ * time if N / K are outside the requested kernel's envelope. */
 int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode);
 
 /* Which feature-extractor (CNN + compress MLP) kernel the planner uses: 0 = automatic (currently always the

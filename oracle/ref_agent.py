@@ -235,6 +235,8 @@ def run_agent_trace(agmod, model, config, batch, case):
     out = {"train_loss": np.float64(ag.summary_writer.scalars[-1][1]),
            "train_logits": rec.calls[0][2].numpy()}
     rec.calls.clear()
+    # the rollout below runs on the parameters / BatchNorm statistics this one optimizer step produced
+    out.update({"after_" + k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()})
     model.eval()
     random.seed(1337)
     with torch.no_grad():

@@ -17,11 +17,11 @@ class Cfg:
         self.num_agents, self.nGraphFilterTaps = n, k
 
 
-def _load(golden):
+def _load(golden, prefix="sd_"):
     import gnn_pathplanning_b200 as gp
     g = golden("agent_trace.npz")
     N, K = int(g["N"]), int(g["K"])
-    sd = {k[3:]: torch.from_numpy(np.ascontiguousarray(g[k])) for k in g.files if k.startswith("sd_")}
+    sd = {k[len(prefix):]: torch.from_numpy(np.ascontiguousarray(g[k])) for k in g.files if k.startswith(prefix)}
     cfg = Cfg(N, K)
     model = gp.DecentralPlannerNet(cfg)             # constructed before config.device exists (:47 vs :86)
     model.load_state_dict(sd)
@@ -48,11 +48,17 @@ def test_train_one_epoch_batch(golden):
     opt.step()
     assert rel_err(torch.stack(predict).detach().cpu().numpy(), g["train_logits"]) <= 1e-5
     assert abs(loss.item() - float(g["train_loss"])) <= 1e-5 * abs(float(g["train_loss"]))
+    # BatchNorm running statistics after the step (the parameters themselves took one Adam step: sign(g) * lr,
+    # which amplifies rounding noise on near-zero gradients and is therefore not compared element-wise)
+    after = model.state_dict()
+    for k in after:
+        if "running" in k:
+            assert rel_err(after[k].double().cpu().numpy(), g["after_" + k]) <= 1e-5, k
 
 
 @pytest.mark.parametrize("gf_mode", ["auto", "tc"])
 def test_rollout_steps(golden, gf_mode):
-    g, cfg, model = _load(golden)
+    g, cfg, model = _load(golden, "after_")        # the agent rolled out with the weights its training step left
     model.eval()
     model.set_graph_filter_mode(gf_mode)
     logsm = torch.nn.LogSoftmax(dim=-1)

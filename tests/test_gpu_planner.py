@@ -198,7 +198,7 @@ def test_train_step_vs_fp64_oracle_at_config_sizes(N, K, B, map_w):
     approximate.  Two correct fp32 implementations may resolve a pre-activation that sits within rounding
     distance of the ReLU kink differently; instead of widening the tolerance the test lists every pre-activation
     within 1e-6 x (layer scale) of zero in the fp64 run, evaluates the fp64 gradients for the natural mask and
-    for single / double flips of exactly those elements, and requires the CUDA gradients to match ONE of those
+    for single flips (the 24 closest) / double flips (the 10 closest) of exactly those elements, and requires the CUDA gradients to match ONE of those
     ground truths -- to within 1e-5, or, where fp32 round-off itself is larger than that, to within 1.5x the
     distance of the reference-order fp32 oracle from its own best-matching ground truth.  Flips are counted and
     printed."""
@@ -225,8 +225,7 @@ def test_train_step_vs_fp64_oracle_at_config_sizes(N, K, B, map_w):
 
     stats = {"kink_tau": 1e-6}
     truths = {(): _oracle_train_step(sd, St, xt, tgt, torch.float64, None, stats)[2]}
-    near = stats.get("near_kink", [])
-    assert len(near) <= 12, "too many pre-activations at the ReLU kink for the flip analysis: %d" % len(near)
+    near = sorted(stats.get("near_kink", []), key=lambda e: abs(e[3]))[:24]       # closest to the kink first
 
     def truth(flips):
         if flips not in truths:
@@ -237,7 +236,7 @@ def test_train_step_vs_fp64_oracle_at_config_sizes(N, K, B, map_w):
         return truths[flips]
 
     def best(got):
-        cands = [()] + [(e,) for e in near] + list(itertools.combinations(near, 2))
+        cands = [()] + [(e,) for e in near] + list(itertools.combinations(near[:10], 2))
         top = (float("inf"), None, None)
         for c in cands:
             e, where = _grad_err(got, truth(c))
