@@ -23,8 +23,9 @@
 //     (TMEM -> registers -> scale, bias, ReLU -> swizzled staging -> TMA tensor store / 128->5 logits) overlaps the
 //     MMAs of tile i+1 and the propagation of tile i+2.
 //
-// Warp roles (448 threads per CTA): 0-7 producers (x -> z_k -> fp16 hi|lo operand rows), 8-11 epilogue (one TMEM lane
-// quarter each), 12 MMA issuer (one lane; leader CTA only) + TMEM allocation + tap load, 13 scout (S staging, scales).
+// Warp roles (640 threads per CTA, 5 warpgroups): 0-11 producers (x -> z_k -> fp16 hi|lo operand rows; 112 registers each
+// after setmaxnreg), 12-15 epilogue (one TMEM lane quarter each), 16 MMA issuer (one lane; leader CTA only) + TMEM
+// allocation + tap load, 17-19 scouts (S staging, scales); the non-producer warpgroups give registers back (72 each).
 // Operand row layout: 128 bytes = [32 x hi | 32 x lo] fp16 of one (tap, 32-feature chunk), SWIZZLE_128B K-major; the
 // three products of a K = 16 step differ only in the descriptors' start offsets (+0 / +64 bytes).
 #include "common.cuh"
@@ -35,21 +36,26 @@
 
 namespace gpp {
 
-constexpr int GP_THREADS = 448;
-constexpr int GP_PROD_WARPS = 8;
-constexpr int GP_EPI_WARP0 = 8;             // warps 8..11: (warp % 4) = TMEM lane quarter
-constexpr int GP_MMA_WARP = 12;
-constexpr int GP_SCOUT_WARP = 13;
+constexpr int GP_THREADS = 640;             // 5 warpgroups: 3 x producers, epilogue, MMA + scouts
+constexpr int GP_PROD_WARPS = 12;           // warps 0..11 (112 registers each after setmaxnreg)
+constexpr int GP_EPI_WARP0 = 12;            // warps 12..15: (warp % 4) = TMEM lane quarter
+constexpr int GP_MMA_WARP = 16;
+constexpr int GP_SCOUT_WARP0 = 17;          // warps 17..19
+// setmaxnreg moves registers inside the CTA's LAUNCH allocation (640 threads x 96 registers = 61,440), not the SM's file:
+// 12 x 32 x 112 + 8 x 32 x 72 = 61,440.  (112 + 88 = 65,536 deadlocks: the third producer warpgroup waits for
+// registers that are never released.)
+constexpr int GP_PROD_REGS = 112;
+constexpr int GP_OTHER_REGS = 72;
+constexpr int GP_SCOUT_WARPS = 3;
 constexpr int GP_M = 128;                   // node rows per CTA tile
 constexpr int GP_C = 128;                   // G = F
 constexpr int GP_NCHUNK = 4;                // 32-feature chunks
-constexpr int GP_AUNIT = GP_M * 128;        // one (tap, chunk) A operand: 16 KB
 constexpr int GP_BUNIT = (GP_C / 2) * 128;  // one (tap, chunk) B operand half: 64 rows, 8 KB
 constexpr int GP_MAX_K = 3;
 constexpr int GP_ACT = 5;
 constexpr int GP_STAGE_BYTES = 2048;        // epilogue staging box: [32 rows][16 cols] fp32
 constexpr int GP_SCALE_RING = 8;            // tiles of per-sample inverse scales kept for the epilogue
-constexpr int GP_MAX_TS = 64;
+constexpr int GP_MAX_TS = 16;              // samples per tile (128 / N, N >= 8)
 constexpr uint32_t GP_IDESC = umma_idesc_f16(2 * GP_M, GP_C);
 constexpr long long GP_WATCHDOG_CYCLES = 1LL << 31;   // ~1 s: a stuck pipeline traps instead of hanging the GPU
 
@@ -65,6 +71,7 @@ struct GpArgs {
     float* logits;            // [N][B][5] or null
     int B, K, TS, num_tiles, num_pairs;
     int s_is_f64, relu, has_act, tail_rows;
+    unsigned long long* timing;   // optional [16] per-role cycle totals (debug option "tc_timing"), null in production
     float wa[GP_ACT * GP_C];  // action MLP (kernel-parameter constant bank: FFMA operands, no loads)
     float ba[8];
 };
@@ -72,16 +79,20 @@ struct GpArgs {
 __host__ __device__ constexpr int gp_np(int N) { return (N + 3) & ~3; }
 
 struct GpSmem {
-    uint32_t b_off, a_off, s_off, s_bytes, stage_off, misc_off, bar_off, total;
+    uint32_t b_off, a_off, a_unit, s_off, s_bytes, stage_off, misc_off, bar_off, total;
     __host__ __device__ GpSmem(int N, int K, int TS) {
         b_off = 0;
         a_off = b_off + (uint32_t)K * GP_NCHUNK * GP_BUNIT;
-        s_off = a_off + 2u * K * GP_AUNIT;
+        // an A operand unit keeps only the 8-row groups that hold tile rows (15 of 16 at N = 10): the MMA still reads
+        // 128 rows, i.e. up to 1 KB past the unit -- the next unit or the S buffers, always inside this allocation --
+        // and what it computes from them lands in accumulator rows nobody reads
+        a_unit = (uint32_t)((TS * N + 7) / 8) * 1024u;
+        s_off = a_off + 2u * K * a_unit;
         s_bytes = (uint32_t)TS * N * gp_np(N) * 4;
         stage_off = (s_off + 2 * s_bytes + 511u) & ~511u;
-        misc_off = stage_off + 4 * 2 * GP_STAGE_BYTES;     // bias[128] | scale_p[2][64] | scale_e[8][64]
+        misc_off = stage_off + 4 * 2 * GP_STAGE_BYTES;     // bias[128] | scale_p[2][TS] | scale_e[8][TS]
         bar_off = misc_off + (GP_C + 2 * GP_MAX_TS + GP_SCALE_RING * GP_MAX_TS) * 4;
-        total = bar_off + 256 + 1024;                      // + alignment slack
+        total = bar_off + 512;
     }
 };
 
@@ -91,16 +102,42 @@ __device__ __noinline__ void gp_watchdog_trap(int id, uint32_t parity) {
            (int)(threadIdx.x >> 5), id, parity);
     __trap();
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the hint
+// elapses) instead of polling -- with plain try_wait loops the seven waiting warps of a CTA executed a third of all
+// issued instructions (profiles/r02_ncu_pair_v2.txt: stall_branch_resolving 2.0, 35.7 K warp instructions per tile).
+constexpr uint32_t GP_SUSPEND_HINT_NS = 1000000;
+__device__ __forceinline__ bool gp_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(GP_SUSPEND_HINT_NS)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool gp_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(GP_SUSPEND_HINT_NS)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void gp_wait(uint64_t* bar, uint32_t parity, int id) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (gp_try_wait(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
+    while (!gp_try_wait(bar, parity))
         if (clock64() - t0 > GP_WATCHDOG_CYCLES) gp_watchdog_trap(id, parity);
 }
 __device__ __forceinline__ void gp_wait_cluster(uint64_t* bar, uint32_t parity, int id) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
+    if (gp_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity))
+    while (!gp_try_wait_cluster(bar, parity))
         if (clock64() - t0 > GP_WATCHDOG_CYCLES) gp_watchdog_trap(id, parity);
 }
 __device__ __forceinline__ void gp_wait_warp(uint64_t* bar, uint32_t parity, int id) {
@@ -148,53 +185,79 @@ __device__ __forceinline__ void gp_propagate(const float* __restrict__ Ss, const
     }
 }
 
-// rows (row0 + n) of one (tap, chunk) operand unit: this lane's 4 features as hi (bytes 8*l8 of the first 64) and lo
+// One (tap, chunk) operand unit: this lane's 4 features of rows row0 + n as hi (8 bytes inside the first 64 of the row)
+// and lo (same place in the second 64: chunk index ^ 4 = byte offset ^ 64 under SWIZZLE_128B).  The shared-memory
+// addresses of both parts are computed once per item (for tap 0) and advanced by one unit per tap.
 template <int N>
-__device__ __forceinline__ void gp_store_tap(unsigned char* unit, int row0, int l8, const float4 (&v)[N]) {
+__device__ __forceinline__ void gp_row_addrs(uint32_t unit0, int row0, int l8, uint32_t (&ahi)[N]) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) ahi[n] = unit0 + sw128_offset(row0 + n, l8 >> 1) + (uint32_t)(l8 & 1) * 8;
+}
+__device__ __forceinline__ void gp_sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void gp_store_tap(const uint32_t (&ahi)[N], const float4 (&v)[N]) {
 #pragma unroll
     for (int n = 0; n < N; ++n) {
         uint2 hi, lo;
         gp_split4(v[n], hi, lo);
-        const int row = row0 + n;
-        const uint32_t sub = (uint32_t)(l8 & 1) * 8;
-        *reinterpret_cast<uint2*>(unit + sw128_offset(row, l8 >> 1) + sub) = hi;
-        *reinterpret_cast<uint2*>(unit + sw128_offset(row, 4 + (l8 >> 1)) + sub) = lo;
+        gp_sts64(ahi[n], hi);
+        gp_sts64(ahi[n] ^ 64u, lo);       // units are 1024-byte aligned: the xor never carries
     }
 }
 
-template <int N>
+template <int N, bool TIMING>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GP_THREADS, 1)
 gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
     constexpr int NP = gp_np(N);
-    extern __shared__ unsigned char gp_smem_raw[];
-    const uint32_t raw = smem_u32(gp_smem_raw);
-    unsigned char* sm = gp_smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    const int K = a.K, TS = a.TS;
+    extern __shared__ __align__(1024) unsigned char gp_smem_raw[];
+    unsigned char* sm = gp_smem_raw;
+    if (threadIdx.x == 0 && (smem_u32(sm) & 1023u) != 0) {
+        printf("gf_fwd_pair_kernel: dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
+    constexpr int TS = GP_M / N;          // samples per 128-row tile
+    const int K = a.K;
     const GpSmem L(N, K, TS);
     float* bias_s = reinterpret_cast<float*>(sm + L.misc_off);
     float* scale_p = bias_s + GP_C;                       // [2][GP_MAX_TS]  2^e per sample (producers)
     float* scale_e = scale_p + 2 * GP_MAX_TS;             // [GP_SCALE_RING][GP_MAX_TS]  2^-e (epilogue)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bar_off);
-    uint64_t* a_full = bars;          // [2] leader: 16 producer warps (both CTAs) stored their rows of the group
-    uint64_t* a_free = bars + 2;      // [2] the MMAs that read the group have completed (multicast commit)
-    uint64_t* acc_full = bars + 4;    // [2] all MMAs of the tile pair have completed (multicast commit)
-    uint64_t* acc_free = bars + 6;    // [2] leader: 8 epilogue warps (both CTAs) have read the accumulator
-    uint64_t* s_full = bars + 8;      // [2] scout staged S + scales of the tile
-    uint64_t* s_free = bars + 10;     // [2] 8 producer warps are done with the S buffer
-    uint64_t* b_full = bars + 12;     // this CTA's tap half has landed
-    uint64_t* b_ready = bars + 13;    // leader: both CTAs' tap halves have landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    // The operand ring is synchronised per (group slot, tap) UNIT, not per group: an item stores tap 0 early and tap
+    // K-1 late, so with per-unit barriers the items of group g+2 start filling the tap-0 unit while the items of
+    // group g are still propagating -- with per-group barriers at most 6 of the 8 producer warps had work
+    // (profiles/r02_pair_phase_v5.txt: 3.4 K cycles per tile waiting for a ring slot).
+    uint64_t* a_full = bars;          // [2*3] leader: the unit's item warps (3 per CTA at N = 10) stored their rows
+    // a_free: the MMAs that read the unit have completed (multicast commit).  FOUR barrier instances per unit, used
+    // round-robin by (group >> 1) & 3: a producer warp only visits the groups it has an item in, and a parity wait
+    // cannot tell "phase n-1 still running" from "phase n complete"; with an instance reused only every 8 groups (a warp
+    // has an item at least every 3) that ambiguity cannot arise.
+    uint64_t* a_free = bars + 6;      // [4][2*3]
+    uint64_t* acc_full = bars + 30;   // [2] all MMAs of the tile pair have completed (multicast commit)
+    uint64_t* acc_free = bars + 32;   // [2] leader: 8 epilogue warps (both CTAs) have read the accumulator
+    uint64_t* s_full = bars + 34;     // [2] the 3 scout warps staged S + scales of the tile
+    uint64_t* s_free = bars + 36;     // [2] 8 producer warps are done with the S buffer
+    uint64_t* b_full = bars + 38;     // this CTA's tap half has landed
+    uint64_t* b_ready = bars + 39;    // leader: both CTAs' tap halves have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const long long t_kernel0 = TIMING ? clock64() : 0;
+    unsigned long long tm[4] = {0, 0, 0, 0};          // per-role cycle totals (lane 0 of one warp per role)
+#define GP_T0() const long long _t0 = TIMING ? clock64() : 0
+#define GP_ACC(i) if (TIMING) tm[i] += (unsigned long long)(clock64() - _t0)
 
     if (tid == 0) {
+        for (int i = 0; i < 2 * GP_MAX_K; ++i) {
+            mbar_init(&a_full[i], 2 * ((TS + 3) / 4));      // the item warps of the unit's group, both CTAs
+            for (int q4 = 0; q4 < 4; ++q4) mbar_init(&a_free[q4 * 2 * GP_MAX_K + i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 2 * GP_PROD_WARPS);
-            mbar_init(&a_free[i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_free[i], 2 * 4);
-            mbar_init(&s_full[i], 1);
+            mbar_init(&s_full[i], GP_SCOUT_WARPS);
             mbar_init(&s_free[i], GP_PROD_WARPS);
         }
         mbar_init(b_full, 1);
@@ -212,7 +275,15 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == GP_MMA_WARP) {
+    // Register re-distribution between the warpgroups (first statement of every role branch, so that the register
+    // limit is unambiguous along each path): the producers hold two generations of 10 x 4 node signals.
+#define GP_REGS_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GP_OTHER_REGS))
+#define GP_REGS_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GP_PROD_REGS))
+
+    const int wg = __shfl_sync(0xffffffffu, warp >> 2, 0);      // warpgroup index (warp-uniform by construction)
+    if (wg == 4) {
+      GP_REGS_DEC();
+      if (warp == GP_MMA_WARP) {
         // =========================== tap load + MMA issuer ===========================
         if (lane == 0) {
             const uint32_t bbytes = (uint32_t)K * GP_NCHUNK * GP_BUNIT;
@@ -224,19 +295,30 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             mbar_arrive_cluster(b_ready, 0);
             if (rank == 0) {
                 gp_wait_cluster(b_ready, 0, 13);
+                if (TIMING) tm[3] = (unsigned long long)(clock64() - t_kernel0);
+                const long long t_loop0 = TIMING ? clock64() : 0;
                 uint32_t g = 0;
                 int t = 0;
                 for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
                     const int buf = t & 1;
-                    if (t >= 2) gp_wait_cluster(&acc_free[buf], ((t >> 1) - 1) & 1, 6 + buf);
+                    if (t >= 2) {
+                        GP_T0();
+                        gp_wait_cluster(&acc_free[buf], ((t >> 1) - 1) & 1, 6 + buf);
+                        GP_ACC(1);
+                    }
                     tcgen05_fence_after();
                     const uint32_t acc = tmem_base + (uint32_t)buf * GP_C;
                     for (int c = 0; c < GP_NCHUNK; ++c, ++g) {
                         const int slot = g & 1;
-                        gp_wait_cluster(&a_full[slot], (g >> 1) & 1, slot);
-                        tcgen05_fence_after();
                         for (int k = 0; k < K; ++k) {
-                            const uint64_t da = umma_desc_sw128(smem_u32(sm + L.a_off + (slot * K + k) * GP_AUNIT));
+                            const int u = slot * GP_MAX_K + k;
+                            {
+                                GP_T0();
+                                gp_wait_cluster(&a_full[u], (g >> 1) & 1, u);
+                                GP_ACC(0);
+                            }
+                            tcgen05_fence_after();
+                            const uint64_t da = umma_desc_sw128(smem_u32(sm + L.a_off + (slot * K + k) * L.a_unit));
                             const uint64_t db = umma_desc_sw128(smem_u32(sm + L.b_off + (k * GP_NCHUNK + c) * GP_BUNIT));
                             // descriptor start offsets in 16-byte units: +2 per K = 16 step, +4 = the lo half of the row
 #pragma unroll
@@ -246,50 +328,71 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                             for (int ks = 0; ks < 2; ++ks) umma_f16_cg2(acc, da + 4 + 2 * ks, db + 2 * ks, GP_IDESC, 1u);
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) umma_f16_cg2(acc, da + 2 * ks, db + 4 + 2 * ks, GP_IDESC, 1u);
+                            umma_commit_cg2(&a_free[((g >> 1) & 3) * 2 * GP_MAX_K + u], 3);
                         }
-                        umma_commit_cg2(&a_free[slot], 3);
                     }
                     umma_commit_cg2(&acc_full[buf], 3);
+                }
+                if (TIMING) tm[2] = (unsigned long long)(clock64() - t_loop0);
+                if (TIMING && a.timing) {
+                    atomicAdd(&a.timing[4], tm[0]); atomicAdd(&a.timing[5], tm[1]); atomicAdd(&a.timing[6], tm[2]);
+                    atomicAdd(&a.timing[13], tm[3]); atomicAdd(&a.timing[11], (unsigned long long)t);
                 }
             }
         }
         __syncwarp();
-    } else if (warp == GP_SCOUT_WARP) {
-        // =========================== scout: S staging + per-sample scales, one tile ahead ===========================
+      } else {
+        // =========================== scouts: S staging + per-sample scales, one tile ahead ===========================
+        // Three warps, each owning every third sample of the tile (10 x 16-byte loads of x + 4 loads of S per lane in
+        // flight) -- one warp doing all 12 samples in turn was the critical path of the whole kernel (33 K cycles per
+        // tile, profiles/r02_pair_phase_v1.txt).
+        const int sw = warp - GP_SCOUT_WARP0;
         int t = 0;
         for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
             const int tile = 2 * p + (int)rank;
             const int s0 = tile * TS;
             const int ns = max(0, min(TS, a.B - s0));
             const int sb = t & 1;
-            if (t >= 2) gp_wait_warp(&s_free[sb], ((t >> 1) - 1) & 1, 10 + sb);
-            float* Sd = reinterpret_cast<float*>(sm + L.s_off + sb * L.s_bytes);
-            const size_t soff = (size_t)s0 * N * N;
-            const int cnt = ns * N * N;
-            if (a.s_is_f64) {
-                const double* Sg = reinterpret_cast<const double*>(a.S) + soff;
-                for (int i = lane; i < cnt; i += 32) {
-                    const int sl = i / (N * N), rem = i - sl * N * N, m = rem / N, n = rem - m * N;
-                    Sd[(sl * N + m) * NP + n] = static_cast<float>(Sg[i]);      // S.float(), graphML.py:2350
-                }
-            } else {
-                const float* Sg = reinterpret_cast<const float*>(a.S) + soff;
-                for (int i = lane; i < cnt; i += 32) {
-                    const int sl = i / (N * N), rem = i - sl * N * N, m = rem / N, n = rem - m * N;
-                    Sd[(sl * N + m) * NP + n] = Sg[i];
-                }
+            if (t >= 2) {
+                GP_T0();
+                gp_wait_warp(&s_free[sb], ((t >> 1) - 1) & 1, 10 + sb);
+                GP_ACC(0);
             }
-            __syncwarp();
-            for (int sl = 0; sl < TS; ++sl) {
+            const long long t_work0 = TIMING ? clock64() : 0;
+            float* Sd = reinterpret_cast<float*>(sm + L.s_off + sb * L.s_bytes);
+            for (int sl = sw; sl < TS; sl += GP_SCOUT_WARPS) {      // one sample at a time: 10 + 4 loads in flight per lane
+                const bool v = sl < ns;
+                float4 xv[N];
+                float se[4];
+                const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+                    xv[n] = v ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const size_t so = (size_t)(s0 + sl) * N * N;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * lane + i;
+                    const bool ve = v && e < N * N;
+                    se[i] = !ve ? 0.f
+                                : (a.s_is_f64 ? static_cast<float>(reinterpret_cast<const double*>(a.S)[so + e])   // S.float(), graphML.py:2350
+                                              : reinterpret_cast<const float*>(a.S)[so + e]);
+                }
+                if (v) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = 4 * lane + i;
+                        if (e < N * N) Sd[(sl * N + e / N) * NP + (e % N)] = se[i];
+                    }
+                }
+                __syncwarp();
                 float e2 = 1.f, e2inv = 1.f;
-                if (sl < ns) {
-                    // largest |x| of the sample (this read is also the L2 prefetch of the tile for the producers)
-                    const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
+                if (v) {
+                    // largest |x| of the sample (the read above is also the L2 prefetch of the tile for the producers)
                     float mx = 0.f;
 #pragma unroll
                     for (int n = 0; n < N; ++n) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C));
-                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                        const float4 q4 = xv[n];
+                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
                     }
                     // largest absolute column sum of S: |z_k[n]| <= max|z_{k-1}| * sum_m |S[m][n]|
                     float cs = 0.f;
@@ -322,8 +425,12 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             }
             __syncwarp();
             if (lane == 0) gp_arrive(&s_full[sb]);
+            if (TIMING) tm[1] += (unsigned long long)(clock64() - t_work0);
         }
-    } else if (warp >= GP_EPI_WARP0) {
+        if (TIMING && a.timing && lane == 0 && sw == 0) { atomicAdd(&a.timing[9], tm[0]); atomicAdd(&a.timing[10], tm[1]); }
+      }
+    } else if (wg == 3) {
+        GP_REGS_DEC();
         // =========================== epilogue: TMEM -> scale, bias, ReLU -> y (TMA store) / logits ===========================
         const int q = warp - GP_EPI_WARP0;
         const int r = q * 32 + lane;                       // TMEM lane = node row of the tile
@@ -338,7 +445,12 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             const int ns = max(0, min(TS, a.B - s0));
             const int R = ns * N;
             const int buf = t & 1;
-            gp_wait_warp(&acc_full[buf], (t >> 1) & 1, 4 + buf);
+            {
+                GP_T0();
+                gp_wait_warp(&acc_full[buf], (t >> 1) & 1, 4 + buf);
+                GP_ACC(0);
+            }
+            const long long t_work0 = TIMING ? clock64() : 0;
             tcgen05_fence_after();
             const bool valid = r < R;
             const int bl = valid ? r / N : 0, n = r - bl * N;
@@ -350,40 +462,55 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             const bool last_tile = tile == a.num_tiles - 1;
             const bool do_store = a.y != nullptr && R > 32 * q;
             float acc5[GP_ACT] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            auto store_chunk = [&](const float (&v)[32], int cb) {
 #pragma unroll
-            for (int cb = 0; cb < 4; ++cb) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GP_C + cb * 32), v);
+                for (int h = 0; h < 2; ++h) {
+                    unsigned char* sbuf = stage + (nstore & 1) * GP_STAGE_BYTES;
+                    if (lane == 0) bulk_wait_group_read<1>();      // the store that last read this buffer is done
+                    __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    v[i] = fmaf(v[i], sc, bias_s[cb * 32 + i]);
-                    if (a.relu) v[i] = fmaxf(v[i], 0.f);
+                    for (int j = 0; j < 4; ++j)                     // SWIZZLE_64B: 16-byte chunk j of row r at j ^ ((r >> 1) & 3)
+                        *reinterpret_cast<float4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                            make_float4(v[h * 16 + 4 * j], v[h * 16 + 4 * j + 1], v[h * 16 + 4 * j + 2], v[h * 16 + 4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && do_store) {
+                        const void* map = (rows_w == 32 || last_tile) ? &a.ymap_full : &a.ymap_tail;
+                        tma_store_2d(map, sbuf, cb * 32 + h * 16, (int)(row0 + 32 * q));
+                    }
+                    if (lane == 0) bulk_commit_group();
+                    ++nstore;
                 }
-                if (a.has_act) {
+            };
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * GP_C);
+            if (a.has_act) {
+                // planner mode: the 128 -> 5 action MLP needs compile-time tap indices (constant-bank FFMA operands)
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    float v[32];
+                    tmem_ld_32x32(tacc + cb * 32, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = fmaf(v[i], sc, bias_s[cb * 32 + i]);
+                        if (a.relu) v[i] = fmaxf(v[i], 0.f);
+                    }
 #pragma unroll
                     for (int o = 0; o < GP_ACT; ++o)
 #pragma unroll
                         for (int i = 0; i < 32; ++i) acc5[o] = fmaf(v[i], a.wa[o * GP_C + cb * 32 + i], acc5[o]);
+                    if (a.y != nullptr) store_chunk(v, cb);
                 }
-                if (a.y != nullptr) {
+            } else {
+#pragma unroll 1
+                for (int cb = 0; cb < 4; ++cb) {
+                    float v[32];
+                    tmem_ld_32x32(tacc + cb * 32, v);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        unsigned char* sbuf = stage + (nstore & 1) * GP_STAGE_BYTES;
-                        if (lane == 0) bulk_wait_group_read<1>();      // the store that last read this buffer is done
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)                     // SWIZZLE_64B: 16-byte chunk j of row r at j ^ ((r >> 1) & 3)
-                            *reinterpret_cast<float4*>(sbuf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
-                                make_float4(v[h * 16 + 4 * j], v[h * 16 + 4 * j + 1], v[h * 16 + 4 * j + 2], v[h * 16 + 4 * j + 3]);
-                        fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && do_store) {
-                            const void* map = (rows_w == 32 || last_tile) ? &a.ymap_full : &a.ymap_tail;
-                            tma_store_2d(map, sbuf, cb * 32 + h * 16, (int)(row0 + 32 * q));
-                        }
-                        if (lane == 0) bulk_commit_group();
-                        ++nstore;
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = fmaf(v[i], sc, bias_s[cb * 32 + i]);
+                        if (a.relu) v[i] = fmaxf(v[i], 0.f);
                     }
+                    store_chunk(v, cb);
                 }
             }
             tcgen05_fence_before();
@@ -394,13 +521,16 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
 #pragma unroll
                 for (int o = 0; o < GP_ACT; ++o) lp[o] = acc5[o] + a.ba[o];
             }
+            if (TIMING) tm[1] += (unsigned long long)(clock64() - t_work0);
         }
         if (lane == 0) bulk_wait_group<0>();
+        if (TIMING && a.timing && lane == 0 && q == 0) { atomicAdd(&a.timing[7], tm[0]); atomicAdd(&a.timing[8], tm[1]); }
     } else {
+        GP_REGS_INC();
         // =========================== producers: x -> z_k -> fp16 hi|lo operand rows ===========================
         const int ql = lane >> 3;          // sample of the item this lane works for
         const int l8 = lane & 7;           // which 4 of the chunk's 32 features
-        const int ipg = (TS + 3) >> 2;     // items (4 samples each) per group
+        const int ipg = (TS + 3) >> 2;     // items (4 samples x 32 features each) per group
         uint32_t g = 0, item_base = 0;
         int t = 0;
         for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
@@ -408,53 +538,86 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             const int s0 = tile * TS;
             const int ns = max(0, min(TS, a.B - s0));
             const int sb = t & 1;
-            gp_wait_warp(&s_full[sb], (t >> 1) & 1, 8 + sb);
+            {
+                GP_T0();
+                gp_wait_warp(&s_full[sb], (t >> 1) & 1, 8 + sb);
+                GP_ACC(0);
+            }
             const float* Ssm = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes);
             for (int c = 0; c < GP_NCHUNK; ++c, ++g) {
                 const int slot = g & 1;
-                bool waited = g < 2;
-                unsigned char* abase = sm + L.a_off + (size_t)slot * K * GP_AUNIT;
+                // before storing into a unit of group g: the MMAs of group g - 2 (same slot) must have completed
+                const uint32_t free_inst = (((g - 2) >> 1) & 3) * 2 * GP_MAX_K, free_parity = ((g - 2) >> 3) & 1;
+                unsigned char* abase = sm + L.a_off + (size_t)slot * K * L.a_unit;
+                int kdone = 0;                      // taps of this group this warp has already signalled
                 for (int j = 0; j < ipg; ++j) {
-                    if (((item_base + (uint32_t)(c * ipg + j)) & (GP_PROD_WARPS - 1)) != (uint32_t)warp) continue;
+                    if ((item_base + (uint32_t)(c * ipg + j)) % GP_PROD_WARPS != (uint32_t)warp) continue;
+                    const long long t_item0 = TIMING ? clock64() : 0;
                     const int sl = j * 4 + ql;
-                    const bool in_tile = sl < TS;
+                    constexpr bool kAllInTile = (TS % 4) == 0;
+                    const bool in_tile = kAllInTile || sl < TS;
                     const bool sv = sl < ns;
                     float4 xv[N];
                     const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + c * 32 + l8 * 4;
 #pragma unroll
                     for (int n = 0; n < N; ++n)
                         xv[n] = sv ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (!waited) {
-                        gp_wait_warp(&a_free[slot], ((g >> 1) - 1) & 1, 2 + slot);
-                        waited = true;
-                    }
                     const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
 #pragma unroll
                     for (int n = 0; n < N; ++n) {
                         xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
                     }
                     const float* Ss = Ssm + (size_t)(in_tile ? sl : 0) * N * NP;
-                    const int row0 = sl * N;
-                    if (in_tile) gp_store_tap<N>(abase, row0, l8, xv);
-                    if (K > 1) {
-                        float4 z[N];
-                        gp_propagate<N>(Ss, xv, z);
-                        if (in_tile) gp_store_tap<N>(abase + GP_AUNIT, row0, l8, z);
-                        if (K > 2) {
-                            gp_propagate<N>(Ss, z, xv);
-                            if (in_tile) gp_store_tap<N>(abase + 2 * GP_AUNIT, row0, l8, xv);
+                    uint32_t ahi[N];
+                    gp_row_addrs<N>(smem_u32(abase), sl * N, l8, ahi);
+                    const bool last_item = true;    // (ipg <= GP_PROD_WARPS: a warp has at most one item per group)
+                    // taps one after the other, loop NOT unrolled: one copy of the propagation + split/store code (the
+                    // fully unrolled item was 27 KB of SASS; with the epilogue it thrashed the 32 KB instruction cache)
+#pragma unroll 1
+                    for (int k = 0; k < K; ++k) {
+                        if (k > 0) {
+                            float4 z[N];
+                            gp_propagate<N>(Ss, xv, z);
+#pragma unroll
+                            for (int n = 0; n < N; ++n) xv[n] = z[n];
+                        }
+                        const int u = slot * GP_MAX_K + k;
+                        if (g >= 2 && kdone <= k) {
+                            GP_T0();
+                            gp_wait_warp(&a_free[free_inst + u], free_parity, 6 + u);
+                            GP_ACC(1);
+                        }
+                        if (in_tile) gp_store_tap<N>(ahi, xv);
+#pragma unroll
+                        for (int n = 0; n < N; ++n) ahi[n] += L.a_unit;
+                        if (last_item) {
+                            fence_proxy_async_smem();       // st.shared operand rows -> visible to the tensor cores
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(&a_full[u], 0);
+                            kdone = k + 1;
                         }
                     }
+                    if (TIMING) {
+                        tm[2] += (unsigned long long)(clock64() - t_item0);
+                        tm[3] += 1;
+                    }
                 }
-                if (!waited) gp_wait_warp(&a_free[slot], ((g >> 1) - 1) & 1, 2 + slot);   // keeps the phases aligned
-                fence_proxy_async_smem();       // st.shared operand rows -> visible to the tensor cores
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&a_full[slot], 0);
+                // Warps without an item in the group do not touch its barriers: an arrival for group g+2 cannot land in
+                // group g's phase of the same unit, because the arriving warp first waited for a_free of that unit, i.e.
+                // for MMAs that were only issued once group g's phase had completed.
             }
             __syncwarp();
             if (lane == 0) gp_arrive(&s_free[sb]);
             item_base += (uint32_t)(GP_NCHUNK * ipg);
         }
+        if (TIMING && a.timing && lane == 0 && warp == 0) {
+            atomicAdd(&a.timing[0], tm[0]); atomicAdd(&a.timing[1], tm[1]); atomicAdd(&a.timing[2], tm[2]);
+            atomicAdd(&a.timing[3], tm[3]);
+        }
+    }
+    if (TIMING && a.timing && tid == 0) {
+        atomicAdd(&a.timing[12], (unsigned long long)(clock64() - t_kernel0));
+        atomicAdd(&a.timing[14], 1ull);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -467,10 +630,11 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
 // tap images: w [F][1][K][G] -> per CTA half (64 output features) K*4 units of 64 rows x 128 bytes [hi 32 | lo 32]
 // fp16 of w * 2^e, SWIZZLE_128B K-major; e from the largest |w| so that |w| * 2^e < 2^15
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) gp_tap_scale_kernel(const float* __restrict__ w, int n, float* __restrict__ wscale) {
+// largest |w| over the taps: one value per thread, block maximum, atomicMax on the (non-negative) float bits
+__global__ void __launch_bounds__(1024) gp_tap_absmax_kernel(const float* __restrict__ w, int n, unsigned int* __restrict__ maxbits) {
     __shared__ float red[32];
-    float mx = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(w[i]));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float mx = i < n ? fabsf(w[i]) : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -479,28 +643,35 @@ __global__ void __launch_bounds__(1024) gp_tap_scale_kernel(const float* __restr
         mx = red[threadIdx.x];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (threadIdx.x == 0) {
-            float s = 1.f, si = 1.f;
-            const int q = (int)((__float_as_uint(mx) >> 23) & 0xFF) - 127;
-            if (mx > 0.f && q < 128) {
-                const int e = max(-100, min(100, 14 - q));
-                s = __uint_as_float((uint32_t)(e + 127) << 23);
-                si = __uint_as_float((uint32_t)(127 - e) << 23);
-            }
-            wscale[0] = s;
-            wscale[1] = si;
-        }
+        if (threadIdx.x == 0) atomicMax(maxbits, __float_as_uint(mx));
+    }
+}
+// 2^e with |w|max * 2^e < 2^15 (and its inverse)
+__device__ __forceinline__ void gp_scale_from_max(float mx, float& s, float& si) {
+    s = 1.f;
+    si = 1.f;
+    const int q = (int)((__float_as_uint(mx) >> 23) & 0xFF) - 127;
+    if (mx > 0.f && q < 128) {
+        const int e = max(-100, min(100, 14 - q));
+        s = __uint_as_float((uint32_t)(e + 127) << 23);
+        si = __uint_as_float((uint32_t)(127 - e) << 23);
     }
 }
 
 __global__ void gp_prep_taps_kernel(const float* __restrict__ w, unsigned char* __restrict__ img,
-                                    const float* __restrict__ wscale, int K) {
+                                    float* __restrict__ wscale, int K) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // one (f, k, g) element each
+    float sc, sci;
+    gp_scale_from_max(__uint_as_float(reinterpret_cast<const unsigned int*>(wscale)[2]), sc, sci);
+    if (idx == 0) {
+        wscale[0] = sc;         // read by the filter kernel's epilogue
+        wscale[1] = sci;
+    }
     if (idx >= GP_C * K * GP_C) return;
     const int f = idx / (K * GP_C), kg = idx - f * (K * GP_C), k = kg / GP_C, gch = kg - k * GP_C;
     const int c = gch >> 5, l = gch & 31;
     const int half = f >> 6, fr = f & 63;
-    const float v = w[idx] * wscale[0];
+    const float v = w[idx] * sc;
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
     unsigned char* unit = img + (size_t)half * K * GP_NCHUNK * GP_BUNIT + (size_t)(k * GP_NCHUNK + c) * GP_BUNIT;
@@ -513,18 +684,22 @@ __global__ void gp_prep_taps_kernel(const float* __restrict__ w, unsigned char* 
 // ---------------------------------------------------------------------------------------
 size_t gf_pair_image_bytes(int K) { return (size_t)2 * K * GP_NCHUNK * GP_BUNIT + 64; }   // + {scale, 1/scale}
 
+// (the producer schedule assumes at most one item per warp per group: ceil(128 / N / 4) <= 8 producer warps)
 bool gf_pair_supported(int N, int K) { return N == 10 && K >= 1 && K <= GP_MAX_K; }
 
 int launch_prep_pair_taps(const float* w, void* img, int K, cudaStream_t st) {
     unsigned char* base = reinterpret_cast<unsigned char*>(img);
     float* wscale = reinterpret_cast<float*>(base + (size_t)2 * K * GP_NCHUNK * GP_BUNIT);
     const int n = GP_C * K * GP_C;
-    gp_tap_scale_kernel<<<1, 1024, 0, st>>>(w, n, wscale);
+    GPP_CUDA_OK(cudaMemsetAsync(wscale, 0, 16, st));
+    gp_tap_absmax_kernel<<<(n + 1023) / 1024, 1024, 0, st>>>(w, n, reinterpret_cast<unsigned int*>(wscale) + 2);
     GPP_LAUNCH_CHECK();
     gp_prep_taps_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, base, wscale, K);
     GPP_LAUNCH_CHECK();
     return GPP_OK;
 }
+
+static unsigned long long* g_pair_timing = nullptr;   // "tc_timing" debug counters
 
 typedef CUresult (*GpEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -573,6 +748,14 @@ int launch_gf_forward_pair(const float* x, const void* S, int s_is_f64, const vo
     a.num_pairs = (a.num_tiles + 1) / 2;
     a.s_is_f64 = s_is_f64; a.relu = relu; a.has_act = wa_host ? 1 : 0;
     a.tail_rows = (TS * N) % 32;
+    a.timing = nullptr;
+    if (debug_option(DBG_TC_TIMING)) {
+        if (!g_pair_timing) {
+            GPP_CUDA_OK(cudaMalloc(&g_pair_timing, 128));
+            GPP_CUDA_OK(cudaMemset(g_pair_timing, 0, 128));
+        }
+        a.timing = g_pair_timing;
+    }
     if (wa_host) {
         for (int i = 0; i < GP_ACT * GP_C; ++i) a.wa[i] = wa_host[i];
         for (int i = 0; i < GP_ACT; ++i) a.ba[i] = ba_host[i];
@@ -585,13 +768,31 @@ int launch_gf_forward_pair(const float* x, const void* S, int s_is_f64, const vo
     }
     const size_t smem = GpSmem(N, K, TS).total;
     GPP_REQUIRE(smem <= 227 * 1024, GPP_ERR_UNSUPPORTED, "gf_forward_pair: %zu bytes of shared memory do not fit", smem);
-    static SmemConfig smem_cfg;
-    GPP_CUDA_OK(ensure_dynamic_smem(gf_fwd_pair_kernel<10>, smem_cfg, smem));
+    static SmemConfig smem_cfg, smem_cfg_t;
     const int max_clusters = sm_count() / 2;
     const int clusters = a.num_pairs < max_clusters ? a.num_pairs : max_clusters;
-    gf_fwd_pair_kernel<10><<<2 * clusters, GP_THREADS, smem, st>>>(a);
+    if (a.timing) {
+        GPP_CUDA_OK(ensure_dynamic_smem(gf_fwd_pair_kernel<10, true>, smem_cfg_t, smem));
+        gf_fwd_pair_kernel<10, true><<<2 * clusters, GP_THREADS, smem, st>>>(a);
+    } else {
+        GPP_CUDA_OK(ensure_dynamic_smem(gf_fwd_pair_kernel<10, false>, smem_cfg, smem));
+        gf_fwd_pair_kernel<10, false><<<2 * clusters, GP_THREADS, smem, st>>>(a);
+    }
     GPP_LAUNCH_CHECK();
     return GPP_OK;
 }
 
 }  // namespace gpp
+
+// debug: per-role cycle totals of gf_fwd_pair_kernel since the last call (filled only with the "tc_timing" option):
+// [0..3] producer warp 0: wait S, wait ring slot, item work, items; [4..6] MMA thread: wait operands, wait accumulator,
+// loop total; [7..8] epilogue warp 0: wait accumulator, work; [9..10] scout: wait S buffer, work; [11] tile pairs
+// (leader MMA threads); [12] kernel cycles (thread 0 of every CTA); [13] leader start-up until the taps landed;
+// [14] CTAs
+extern "C" int gpp_debug_pair_timing(unsigned long long* out16) {
+    if (!gpp::g_pair_timing) return GPP_ERR_INVALID;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out16, gpp::g_pair_timing, 128, cudaMemcpyDeviceToHost);
+    cudaMemset(gpp::g_pair_timing, 0, 128);
+    return GPP_OK;
+}

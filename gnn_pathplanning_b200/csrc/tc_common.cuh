@@ -155,12 +155,16 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// arrive (count 1, release at cluster scope) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+// arrive (count 1) on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster.  Default semantics
+// (release at CTA scope), as CUTLASS' ClusterBarrier::arrive(cta_id) uses for the same purpose: an explicit
+// .release.cluster compiles to MEMBAR + ERRBAR in front of every arrive (~700 cycles per producer warp per group,
+// profiles/r02_ncu_pair_v2_source_top.txt).  What the peer's tensor core reads (operand rows in the peer's own shared
+// memory) is ordered by the writers' fence.proxy.async before this arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(cta)
         : "memory");
 }

@@ -23,6 +23,11 @@ int gpp_debug_umma_selftest(const float* A, const float* B, float* D, void* stre
 
 /* Debug: per-phase cycle totals of the tcgen05 filter kernel (filled only when the "tc_timing" option is set): staging loop, wait for the last MMA, TMEM read-out, propagation, stores, tiles. */
 int gpp_debug_tc_timing(unsigned long long* out6);
+/* Per-role cycle totals of the CTA-pair tcgen05 filter kernel ("tc_timing"): [0..3] producer warp 0 of every CTA: wait
+ * for S, wait for a ring slot, item work, items; [4..6] leader MMA threads: wait for operands, wait for the accumulator,
+ * loop total; [7..8] epilogue warp 0: wait, work; [9..10] scout: wait, work; [11] tile pairs; [12] kernel cycles
+ * (thread 0 of every CTA); [13] leader start-up until the taps landed; [14] CTAs. */
+int gpp_debug_pair_timing(unsigned long long* out16);
 /* Same for block 0 of the CUDA-core filter kernel ("gf_timing"): prologue, x/S staging,
  * propagation, tap contraction, epilogue, action MLP + column-half merge. */
 int gpp_debug_gf_timing(unsigned long long* out6);

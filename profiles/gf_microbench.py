@@ -47,11 +47,11 @@ if __name__ == "__main__":
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    for mode, name in ((1, "cuda-core"), (2, "tcgen05")):
+    for mode, name in ((1, "cuda-core"), (2, "tcgen05-tf32"), (3, "tcgen05-pair")):
         r = subprocess.run([sys.executable, "-c", CHILD % ROOT, str(N), str(K), str(mode)], capture_output=True, text=True)
         if r.returncode != 0:
             print(name, "FAILED", r.stderr[-400:])
             continue
         for row in json.loads(r.stdout.strip().splitlines()[-1]):
-            print("%-10s N=%d K=%d B=%6d  %9.1f us  %8.2f M agent-steps/s  %7.1f GB/s algorithmic = %.3f of HBM peak (incl. tap prep launch)"
+            print("%-12s N=%d K=%d B=%6d  %9.1f us  %8.2f M agent-steps/s  %7.1f GB/s algorithmic = %.3f of HBM peak (incl. tap prep launch)"
                   % (name, N, K, row["B"], row["us"], row["agent_steps_per_s"] / 1e6, row["alg_GBps"], row["alg_GBps"] / peak))
