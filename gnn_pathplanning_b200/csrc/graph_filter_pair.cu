@@ -23,9 +23,9 @@
 //     (TMEM -> registers -> scale, bias, ReLU -> swizzled staging -> TMA tensor store / 128->5 logits) overlaps the
 //     MMAs of tile i+1 and the propagation of tile i+2.
 //
-// Warp roles (640 threads per CTA, 5 warpgroups): 0-11 producers (x -> z_k -> fp16 hi|lo operand rows; 112 registers each
-// after setmaxnreg), 12-15 epilogue (one TMEM lane quarter each), 16 MMA issuer (one lane; leader CTA only) + TMEM
-// allocation + tap load, 17-19 scouts (S staging, scales); the non-producer warpgroups give registers back (72 each).
+// Warp roles (512 threads per CTA): 0-5 producers (x -> z_k -> fp16 hi|lo operand rows), 6 MMA issuer (one lane; leader
+// CTA only) + TMEM allocation + tap load, 8-11 epilogue (one TMEM lane quarter each), 7 and 12-15 scouts (S and S.S
+// staging, scales).
 // Operand row layout: 128 bytes = [32 x hi | 32 x lo] fp16 of one (tap, 32-feature chunk), SWIZZLE_128B K-major; the
 // three products of a K = 16 step differ only in the descriptors' start offsets (+0 / +64 bytes).
 #include "common.cuh"
@@ -36,17 +36,11 @@
 
 namespace gpp {
 
-constexpr int GP_THREADS = 640;             // 5 warpgroups: 3 x producers, epilogue, MMA + scouts
-constexpr int GP_PROD_WARPS = 12;           // warps 0..11 (112 registers each after setmaxnreg)
-constexpr int GP_EPI_WARP0 = 12;            // warps 12..15: (warp % 4) = TMEM lane quarter
-constexpr int GP_MMA_WARP = 16;
-constexpr int GP_SCOUT_WARP0 = 17;          // warps 17..19
-// setmaxnreg moves registers inside the CTA's LAUNCH allocation (640 threads x 96 registers = 61,440), not the SM's file:
-// 12 x 32 x 112 + 8 x 32 x 72 = 61,440.  (112 + 88 = 65,536 deadlocks: the third producer warpgroup waits for
-// registers that are never released.)
-constexpr int GP_PROD_REGS = 112;
-constexpr int GP_OTHER_REGS = 72;
-constexpr int GP_SCOUT_WARPS = 3;
+constexpr int GP_THREADS = 512;
+constexpr int GP_PROD_WARPS = 6;            // warps 0..5: exactly the 2 ring groups x 3 items that can be in flight
+constexpr int GP_MMA_WARP = 6;
+constexpr int GP_EPI_WARP0 = 8;             // warps 8..11: (warp % 4) = TMEM lane quarter
+constexpr int GP_SCOUT_WARPS = 5;           // warps 7, 12..15
 constexpr int GP_M = 128;                   // node rows per CTA tile
 constexpr int GP_C = 128;                   // G = F
 constexpr int GP_NCHUNK = 4;                // 32-feature chunks
@@ -71,12 +65,19 @@ struct GpArgs {
     float* logits;            // [N][B][5] or null
     int B, K, TS, num_tiles, num_pairs;
     int s_is_f64, relu, has_act, tail_rows;
+    int ablate;               // debug ("pair_ablate"): 1 skip the propagations, 2 skip the operand stores, 4 skip the x loads, 8 skip the y stores
     unsigned long long* timing;   // optional [16] per-role cycle totals (debug option "tc_timing"), null in production
     float wa[GP_ACT * GP_C];  // action MLP (kernel-parameter constant bank: FFMA operands, no loads)
     float ba[8];
 };
 
-__host__ __device__ constexpr int gp_np(int N) { return (N + 3) & ~3; }
+// Row m of a staged GSO (or of S.S) holds the N coefficients of z[n] += S[m][n] x[m] in two blocks, one per half of the
+// output nodes: [n = 0 .. NA-1 | pad to 4 | n = NA .. N-1 | pad to 4]  (N = 10: NA = 6 -> 12 floats: a 16-byte + an 8-byte
+// load for the first half, one 16-byte load for the second).
+__host__ __device__ constexpr int gp_na(int N) { return (N + 2) / 2 <= 4 ? (N < 4 ? N : 4) : (N + 2) / 2; }
+__host__ __device__ constexpr int gp_slot_b(int N) { return (gp_na(N) + 3) & ~3; }
+__host__ __device__ constexpr int gp_np(int N) { return gp_slot_b(N) + ((N - gp_na(N) + 3) & ~3); }
+__host__ __device__ constexpr int gp_slot(int N, int n) { return n < gp_na(N) ? n : gp_slot_b(N) + (n - gp_na(N)); }
 
 struct GpSmem {
     uint32_t b_off, a_off, a_unit, s_off, s_bytes, stage_off, misc_off, bar_off, total;
@@ -88,7 +89,7 @@ struct GpSmem {
         // and what it computes from them lands in accumulator rows nobody reads
         a_unit = (uint32_t)((TS * N + 7) / 8) * 1024u;
         s_off = a_off + 2u * K * a_unit;
-        s_bytes = (uint32_t)TS * N * gp_np(N) * 4;
+        s_bytes = (uint32_t)TS * N * gp_np(N) * 4 * (K > 2 ? 2 : 1);   // per buffer: S, then S.S (third tap)
         stage_off = (s_off + 2 * s_bytes + 511u) & ~511u;
         misc_off = stage_off + 4 * 2 * GP_STAGE_BYTES;     // bias[128] | scale_p[2][TS] | scale_e[8][TS]
         bar_off = misc_off + (GP_C + 2 * GP_MAX_TS + GP_SCALE_RING * GP_MAX_TS) * 4;
@@ -159,35 +160,35 @@ __device__ __forceinline__ void gp_split4(const float4 v, uint2& hi, uint2& lo) 
     lo.y = *reinterpret_cast<const uint32_t*>(&l23);
 }
 
-// out[n] = sum_m S[m][n] * in[m]   (z_k = z_{k-1} . S, graphML.py:2350; 4 features per lane)
-template <int N>
-__device__ __forceinline__ void gp_propagate(const float* __restrict__ Ss, const float4 (&in)[N], float4 (&out)[N]) {
+// out[i] = sum_m M[m][N0 + i] * in[m] for the CNT output nodes starting at N0 (z = x . M with M = S or S.S,
+// graphML.py:2350; 4 features per lane).  SLOT0 = position of coefficient N0 inside a staged row.
+template <int N, int N0, int CNT, int SLOT0>
+__device__ __forceinline__ void gp_propagate_half(const float* __restrict__ Ms, const float4 (&in)[N], float4 (&out)[CNT]) {
     constexpr int NP = gp_np(N);
 #pragma unroll
-    for (int n = 0; n < N; ++n) out[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < CNT; ++i) out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int m = 0; m < N; ++m) {
+        float sv[(CNT + 3) & ~3];
 #pragma unroll
-        for (int q = 0; q < NP / 4; ++q) {
-            const float4 s4 = ld_smem4(Ss + m * NP + 4 * q);
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int n = 4 * q + i;
-                if (n < N) {
-                    out[n].x = fmaf(sv[i], in[m].x, out[n].x);
-                    out[n].y = fmaf(sv[i], in[m].y, out[n].y);
-                    out[n].z = fmaf(sv[i], in[m].z, out[n].z);
-                    out[n].w = fmaf(sv[i], in[m].w, out[n].w);
-                }
+        for (int q = 0; q < (CNT + 3) / 4; ++q) {
+            if (CNT - 4 * q >= 3) {
+                const float4 s4 = ld_smem4(Ms + m * NP + SLOT0 + 4 * q);
+                sv[4 * q] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
+            } else {
+                const float2 s2 = *reinterpret_cast<const float2*>(Ms + m * NP + SLOT0 + 4 * q);
+                sv[4 * q] = s2.x; sv[4 * q + 1] = s2.y;
             }
+        }
+#pragma unroll
+        for (int i = 0; i < CNT; ++i) {
+            out[i].x = fmaf(sv[i], in[m].x, out[i].x);
+            out[i].y = fmaf(sv[i], in[m].y, out[i].y);
+            out[i].z = fmaf(sv[i], in[m].z, out[i].z);
+            out[i].w = fmaf(sv[i], in[m].w, out[i].w);
         }
     }
 }
-
-// One (tap, chunk) operand unit: this lane's 4 features of rows row0 + n as hi (8 bytes inside the first 64 of the row)
-// and lo (same place in the second 64: chunk index ^ 4 = byte offset ^ 64 under SWIZZLE_128B).  The shared-memory
-// addresses of both parts are computed once per item (for tap 0) and advanced by one unit per tap.
 template <int N>
 __device__ __forceinline__ void gp_row_addrs(uint32_t unit0, int row0, int l8, uint32_t (&ahi)[N]) {
 #pragma unroll
@@ -196,14 +197,16 @@ __device__ __forceinline__ void gp_row_addrs(uint32_t unit0, int row0, int l8, u
 __device__ __forceinline__ void gp_sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
-template <int N>
-__device__ __forceinline__ void gp_store_tap(const uint32_t (&ahi)[N], const float4 (&v)[N]) {
+// rows N0 .. N0+CNT-1 of the item's sample: split and store this lane's 4 features
+template <int N, int N0, int CNT>
+__device__ __forceinline__ void gp_store_rows(const uint32_t (&ahi)[N], uint32_t tap_off, const float4 (&v)[CNT]) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) {
+    for (int i = 0; i < CNT; ++i) {
         uint2 hi, lo;
-        gp_split4(v[n], hi, lo);
-        gp_sts64(ahi[n], hi);
-        gp_sts64(ahi[n] ^ 64u, lo);       // units are 1024-byte aligned: the xor never carries
+        gp_split4(v[i], hi, lo);
+        const uint32_t addr = ahi[N0 + i] + tap_off;
+        gp_sts64(addr, hi);
+        gp_sts64(addr ^ 64u, lo);         // units are 1024-byte aligned: the xor never carries
     }
 }
 
@@ -224,23 +227,20 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
     float* scale_p = bias_s + GP_C;                       // [2][GP_MAX_TS]  2^e per sample (producers)
     float* scale_e = scale_p + 2 * GP_MAX_TS;             // [GP_SCALE_RING][GP_MAX_TS]  2^-e (epilogue)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.bar_off);
-    // The operand ring is synchronised per (group slot, tap) UNIT, not per group: an item stores tap 0 early and tap
-    // K-1 late, so with per-unit barriers the items of group g+2 start filling the tap-0 unit while the items of
-    // group g are still propagating -- with per-group barriers at most 6 of the 8 producer warps had work
-    // (profiles/r02_pair_phase_v5.txt: 3.4 K cycles per tile waiting for a ring slot).
-    uint64_t* a_full = bars;          // [2*3] leader: the unit's item warps (3 per CTA at N = 10) stored their rows
-    // a_free: the MMAs that read the unit have completed (multicast commit).  FOUR barrier instances per unit, used
-    // round-robin by (group >> 1) & 3: a producer warp only visits the groups it has an item in, and a parity wait
-    // cannot tell "phase n-1 still running" from "phase n complete"; with an instance reused only every 8 groups (a warp
-    // has an item at least every 3) that ambiguity cannot arise.
-    uint64_t* a_free = bars + 6;      // [4][2*3]
-    uint64_t* acc_full = bars + 30;   // [2] all MMAs of the tile pair have completed (multicast commit)
-    uint64_t* acc_free = bars + 32;   // [2] leader: 8 epilogue warps (both CTAs) have read the accumulator
-    uint64_t* s_full = bars + 34;     // [2] the 3 scout warps staged S + scales of the tile
-    uint64_t* s_free = bars + 36;     // [2] 8 producer warps are done with the S buffer
-    uint64_t* b_full = bars + 38;     // this CTA's tap half has landed
-    uint64_t* b_ready = bars + 39;    // leader: both CTAs' tap halves have landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+    // Ring barriers are per group slot.  Only the warps that have an item in a group touch its barriers (3 per CTA at
+    // N = 10), so a warp never waits on groups it has no work in.  a_free has FOUR instances per slot, used round-robin
+    // by (group >> 1) & 3: a warp that only visits every fourth group cannot tell "phase n-1 still running" from
+    // "phase n complete" with a parity wait on a barrier that completes every other group; with an instance that is
+    // reused only every 8 groups the ambiguity cannot arise.
+    uint64_t* a_full = bars;          // [2] leader: the group's item warps (both CTAs) stored all taps of their rows
+    uint64_t* a_free = bars + 2;      // [4][2] the MMAs that read the group have completed (multicast commit)
+    uint64_t* acc_full = bars + 10;   // [2] all MMAs of the tile pair have completed (multicast commit)
+    uint64_t* acc_free = bars + 12;   // [2] leader: 8 epilogue warps (both CTAs) have read the accumulator
+    uint64_t* s_full = bars + 14;     // [2] the 3 scout warps staged S (+ S.S) + scales of the tile
+    uint64_t* s_free = bars + 16;     // [2] 12 producer warps are done with the S buffer
+    uint64_t* b_full = bars + 18;     // this CTA's tap half has landed
+    uint64_t* b_ready = bars + 19;    // leader: both CTAs' tap halves have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -250,11 +250,9 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
 #define GP_ACC(i) if (TIMING) tm[i] += (unsigned long long)(clock64() - _t0)
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * GP_MAX_K; ++i) {
-            mbar_init(&a_full[i], 2 * ((TS + 3) / 4));      // the item warps of the unit's group, both CTAs
-            for (int q4 = 0; q4 < 4; ++q4) mbar_init(&a_free[q4 * 2 * GP_MAX_K + i], 1);
-        }
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 2 * ((TS + 3) / 4));      // the item warps of the group, both CTAs
+            for (int q4 = 0; q4 < 4; ++q4) mbar_init(&a_free[q4 * 2 + i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_free[i], 2 * 4);
             mbar_init(&s_full[i], GP_SCOUT_WARPS);
@@ -275,14 +273,8 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Register re-distribution between the warpgroups (first statement of every role branch, so that the register
-    // limit is unambiguous along each path): the producers hold two generations of 10 x 4 node signals.
-#define GP_REGS_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GP_OTHER_REGS))
-#define GP_REGS_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GP_PROD_REGS))
-
-    const int wg = __shfl_sync(0xffffffffu, warp >> 2, 0);      // warpgroup index (warp-uniform by construction)
-    if (wg == 4) {
-      GP_REGS_DEC();
+    const bool is_scout = warp == 7 || warp >= 12;
+    if (warp == GP_MMA_WARP || is_scout) {
       if (warp == GP_MMA_WARP) {
         // =========================== tap load + MMA issuer ===========================
         if (lane == 0) {
@@ -310,14 +302,13 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                     const uint32_t acc = tmem_base + (uint32_t)buf * GP_C;
                     for (int c = 0; c < GP_NCHUNK; ++c, ++g) {
                         const int slot = g & 1;
+                        {
+                            GP_T0();
+                            gp_wait_cluster(&a_full[slot], (g >> 1) & 1, slot);
+                            GP_ACC(0);
+                        }
+                        tcgen05_fence_after();
                         for (int k = 0; k < K; ++k) {
-                            const int u = slot * GP_MAX_K + k;
-                            {
-                                GP_T0();
-                                gp_wait_cluster(&a_full[u], (g >> 1) & 1, u);
-                                GP_ACC(0);
-                            }
-                            tcgen05_fence_after();
                             const uint64_t da = umma_desc_sw128(smem_u32(sm + L.a_off + (slot * K + k) * L.a_unit));
                             const uint64_t db = umma_desc_sw128(smem_u32(sm + L.b_off + (k * GP_NCHUNK + c) * GP_BUNIT));
                             // descriptor start offsets in 16-byte units: +2 per K = 16 step, +4 = the lo half of the row
@@ -328,8 +319,8 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                             for (int ks = 0; ks < 2; ++ks) umma_f16_cg2(acc, da + 4 + 2 * ks, db + 2 * ks, GP_IDESC, 1u);
 #pragma unroll
                             for (int ks = 0; ks < 2; ++ks) umma_f16_cg2(acc, da + 2 * ks, db + 4 + 2 * ks, GP_IDESC, 1u);
-                            umma_commit_cg2(&a_free[((g >> 1) & 3) * 2 * GP_MAX_K + u], 3);
                         }
+                        umma_commit_cg2(&a_free[((g >> 1) & 3) * 2 + slot], 3);
                     }
                     umma_commit_cg2(&acc_full[buf], 3);
                 }
@@ -343,10 +334,10 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         __syncwarp();
       } else {
         // =========================== scouts: S staging + per-sample scales, one tile ahead ===========================
-        // Three warps, each owning every third sample of the tile (10 x 16-byte loads of x + 4 loads of S per lane in
-        // flight) -- one warp doing all 12 samples in turn was the critical path of the whole kernel (33 K cycles per
-        // tile, profiles/r02_pair_phase_v1.txt).
-        const int sw = warp - GP_SCOUT_WARP0;
+        // Five warps, each owning every fifth sample of the tile -- one warp doing all 12 samples in turn was the critical
+        // path of the whole kernel (33 K cycles per tile, profiles/r02_pair_phase_v1.txt), three warps with one sample
+        // in flight still took 7 us per tile (profiles/r02_pair_ablation_v10.txt: "pipeline skeleton").
+        const int sw = warp == 7 ? 0 : warp - 11;      // scout index 0..4
         int t = 0;
         for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
             const int tile = 2 * p + (int)rank;
@@ -360,67 +351,95 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             }
             const long long t_work0 = TIMING ? clock64() : 0;
             float* Sd = reinterpret_cast<float*>(sm + L.s_off + sb * L.s_bytes);
-            for (int sl = sw; sl < TS; sl += GP_SCOUT_WARPS) {      // one sample at a time: 10 + 4 loads in flight per lane
-                const bool v = sl < ns;
-                float4 xv[N];
-                float se[4];
-                const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
+            for (int sl0 = sw; sl0 < TS; sl0 += 2 * GP_SCOUT_WARPS) {
+                // two samples (2 x (10 + 4) loads per lane) in flight: this role is latency-bound -- one DRAM round trip
+                // per batch of loads -- and, one tile ahead of everything else, it paces the whole pipeline
+                float4 xv[2][N];
+                float se[2][4];
 #pragma unroll
-                for (int n = 0; n < N; ++n)
-                    xv[n] = v ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const size_t so = (size_t)(s0 + sl) * N * N;
+                for (int h = 0; h < 2; ++h) {
+                    const int sl = sl0 + h * GP_SCOUT_WARPS;
+                    const bool v = sl < ns;
+                    const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int e = 4 * lane + i;
-                    const bool ve = v && e < N * N;
-                    se[i] = !ve ? 0.f
-                                : (a.s_is_f64 ? static_cast<float>(reinterpret_cast<const double*>(a.S)[so + e])   // S.float(), graphML.py:2350
-                                              : reinterpret_cast<const float*>(a.S)[so + e]);
-                }
-                if (v) {
+                    for (int n = 0; n < N; ++n)
+                        xv[h][n] = v ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const size_t so = (size_t)(s0 + sl) * N * N;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int e = 4 * lane + i;
-                        if (e < N * N) Sd[(sl * N + e / N) * NP + (e % N)] = se[i];
+                        const bool ve = v && e < N * N;
+                        se[h][i] = !ve ? 0.f
+                                       : (a.s_is_f64 ? static_cast<float>(reinterpret_cast<const double*>(a.S)[so + e])   // S.float(), graphML.py:2350
+                                                     : reinterpret_cast<const float*>(a.S)[so + e]);
                     }
                 }
-                __syncwarp();
-                float e2 = 1.f, e2inv = 1.f;
-                if (v) {
-                    // largest |x| of the sample (the read above is also the L2 prefetch of the tile for the producers)
-                    float mx = 0.f;
 #pragma unroll
-                    for (int n = 0; n < N; ++n) {
-                        const float4 q4 = xv[n];
-                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
-                    }
-                    // largest absolute column sum of S: |z_k[n]| <= max|z_{k-1}| * sum_m |S[m][n]|
-                    float cs = 0.f;
-                    if (lane < N) {
+                for (int h = 0; h < 2; ++h) {
+                    const int sl = sl0 + h * GP_SCOUT_WARPS;
+                    if (sl >= TS) continue;
+                    const bool v = sl < ns;
+                    if (v) {
 #pragma unroll
-                        for (int m = 0; m < N; ++m) cs += fabsf(Sd[(sl * N + m) * NP + lane]);
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = 4 * lane + i;
+                            if (e < N * N) Sd[(sl * N + e / N) * NP + gp_slot(N, e % N)] = se[h][i];
+                        }
                     }
+                    __syncwarp();
+                    float e2 = 1.f, e2inv = 1.f;
+                    if (v) {
+                        // largest |x| of the sample (the read above is also the L2 prefetch of the tile for the producers)
+                        float mx = 0.f;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                        cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, o));
+                        for (int n = 0; n < N; ++n) {
+                            const float4 q4 = xv[h][n];
+                            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
+                        }
+                        // largest absolute column sum of S: |z_k[n]| <= max|z_{k-1}| * sum_m |S[m][n]|
+                        float cs = 0.f;
+                        if (lane < N) {
+#pragma unroll
+                            for (int m = 0; m < N; ++m) cs += fabsf(Sd[(sl * N + m) * NP + gp_slot(N, lane)]);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                            cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, o));
+                        }
+                        float bound = mx;
+                        const float cm = fmaxf(cs, 1.f);
+                        for (int k = 1; k < K; ++k) bound *= cm;
+                        // bound in [2^q, 2^(q+1)): scale by 2^(14-q) so that every |z_k| * scale < 2^15 (fp16 max 65504)
+                        const uint32_t bits = __float_as_uint(bound);
+                        const int q = (int)((bits >> 23) & 0xFF) - 127;
+                        if (bound > 0.f && q < 128) {
+                            int e = 14 - q;
+                            e = max(-100, min(100, e));
+                            e2 = __uint_as_float((uint32_t)(e + 127) << 23);
+                            e2inv = __uint_as_float((uint32_t)(127 - e) << 23);
+                        }
                     }
-                    float bound = mx;
-                    const float cm = fmaxf(cs, 1.f);
-                    for (int k = 1; k < K; ++k) bound *= cm;
-                    // bound in [2^q, 2^(q+1)): scale by 2^(14-q) so that every |z_k| * scale < 2^15 (fp16 max 65504)
-                    const uint32_t bits = __float_as_uint(bound);
-                    const int q = (int)((bits >> 23) & 0xFF) - 127;
-                    if (bound > 0.f && q < 128) {
-                        int e = 14 - q;
-                        e = max(-100, min(100, e));
-                        e2 = __uint_as_float((uint32_t)(e + 127) << 23);
-                        e2inv = __uint_as_float((uint32_t)(127 - e) << 23);
+                    if (lane == 0) {
+                        scale_p[sb * GP_MAX_TS + sl] = e2;
+                        scale_e[(t & (GP_SCALE_RING - 1)) * GP_MAX_TS + sl] = e2inv;
                     }
-                }
-                if (lane == 0) {
-                    scale_p[sb * GP_MAX_TS + sl] = e2;
-                    scale_e[(t & (GP_SCALE_RING - 1)) * GP_MAX_TS + sl] = e2inv;
+                    if (K > 2 && v) {
+                        // S.S for the third tap: z_2 = (x.S).S = x.(S.S), so the producers form every tap straight from x
+                        float* S2d = Sd + TS * N * NP;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = 4 * lane + i;
+                            if (e < N * N) {
+                                const int m = e / N, n = e % N;
+                                float acc = 0.f;
+#pragma unroll
+                                for (int jj = 0; jj < N; ++jj)
+                                    acc = fmaf(Sd[(sl * N + m) * NP + gp_slot(N, jj)], Sd[(sl * N + jj) * NP + gp_slot(N, n)], acc);
+                                S2d[(sl * N + m) * NP + gp_slot(N, n)] = acc;
+                            }
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -429,9 +448,8 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         }
         if (TIMING && a.timing && lane == 0 && sw == 0) { atomicAdd(&a.timing[9], tm[0]); atomicAdd(&a.timing[10], tm[1]); }
       }
-    } else if (wg == 3) {
-        GP_REGS_DEC();
-        // =========================== epilogue: TMEM -> scale, bias, ReLU -> y (TMA store) / logits ===========================
+    } else if (warp >= GP_EPI_WARP0) {
+          // =========================== epilogue: TMEM -> scale, bias, ReLU -> y (TMA store) / logits ===========================
         const int q = warp - GP_EPI_WARP0;
         const int r = q * 32 + lane;                       // TMEM lane = node row of the tile
         unsigned char* stage = sm + L.stage_off + q * 2 * GP_STAGE_BYTES;
@@ -460,7 +478,7 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             // the tensor map's row extent instead (rows past B*N are never written)
             const int rows_w = max(0, min(32, full_rows - 32 * q));
             const bool last_tile = tile == a.num_tiles - 1;
-            const bool do_store = a.y != nullptr && R > 32 * q;
+            const bool do_store = a.y != nullptr && R > 32 * q && !(a.ablate & 8);
             float acc5[GP_ACT] = {0.f, 0.f, 0.f, 0.f, 0.f};
             auto store_chunk = [&](const float (&v)[32], int cb) {
 #pragma unroll
@@ -526,89 +544,111 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         if (lane == 0) bulk_wait_group<0>();
         if (TIMING && a.timing && lane == 0 && q == 0) { atomicAdd(&a.timing[7], tm[0]); atomicAdd(&a.timing[8], tm[1]); }
     } else {
-        GP_REGS_INC();
         // =========================== producers: x -> z_k -> fp16 hi|lo operand rows ===========================
-        const int ql = lane >> 3;          // sample of the item this lane works for
-        const int l8 = lane & 7;           // which 4 of the chunk's 32 features
-        const int ipg = (TS + 3) >> 2;     // items (4 samples x 32 features each) per group
-        uint32_t g = 0, item_base = 0;
-        int t = 0;
-        for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
-            const int tile = 2 * p + (int)rank;
-            const int s0 = tile * TS;
-            const int ns = max(0, min(TS, a.B - s0));
-            const int sb = t & 1;
+        // An item = 4 samples x one 32-feature chunk of one tile: lane (ql, l8) owns features 4*l8 .. 4*l8+3 of all N
+        // nodes of sample ql.  Every tap is formed straight from x (z_1 = x.S, z_2 = x.(S.S)), one half of the output
+        // nodes at a time, so the live state is x (N x 4) + half a tap ((N+2)/2 x 4) + N row addresses.
+        constexpr int NA = gp_na(N), NB = N - NA, SLOT_B = gp_slot_b(N);
+        constexpr int ipg = (TS + 3) >> 2;             // items per group
+        constexpr int ipt = ipg * GP_NCHUNK;           // items per tile
+        static_assert(2 * ipg == GP_PROD_WARPS, "producer warps = the items of the two ring groups");
+        static_assert((TS % 4) == 0, "item = 4 whole samples");
+        // Item I (global sequence of this CTA) = (tile I / ipt, chunk (I % ipt) / ipg, sample quad (I % ipt) % ipg); warp w
+        // takes I = w, w + 6, ...: its quad is w % 3 and its groups all have parity w / 3, i.e. ONE ring slot for good.
+        // What bounds the kernel is the latency of one item (a slot is busy from the first operand store until the MMAs
+        // that read it have completed), so the x rows of the NEXT item are fetched into registers while this one runs.
+        const int ql = lane >> 3;
+        const int l8 = lane & 7;
+        const int jq = warp % ipg;
+        const int slot = warp / ipg;
+        const int sl = jq * 4 + ql;                    // sample of the tile this lane works for, in every item
+        int ntile_seq = 0;
+        for (int p = cluster_id; p < a.num_pairs; p += num_clusters) ++ntile_seq;
+        const int total_items = ntile_seq * ipt;
+        uint32_t ahi0[N];                              // operand row addresses of tap 0 (same rows, same slot every item)
+        gp_row_addrs<N>(smem_u32(sm + L.a_off + (size_t)slot * K * L.a_unit), sl * N, l8, ahi0);
+        auto item_ptr = [&](int I) -> const float* {
+            const int tt = I / ipt, c = (I - tt * ipt) / ipg;
+            const int tile = 2 * (cluster_id + tt * num_clusters) + (int)rank;
+            const int smp = tile * TS + sl;
+            return smp < a.B ? a.x + ((size_t)smp * N) * GP_C + c * 32 + l8 * 4 : nullptr;
+        };
+        float4 xn[N];
+        {
+            const float* xp = warp < total_items ? item_ptr(warp) : nullptr;
+#pragma unroll
+            for (int n = 0; n < N; ++n)
+                xn[n] = (xp && !(a.ablate & 4)) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        int cur_tile = -1;
+        for (int I = warp; I < total_items; I += GP_PROD_WARPS) {
+            const long long t_item0 = TIMING ? clock64() : 0;
+            const int tt = I / ipt, c = (I - tt * ipt) / ipg;
+            const uint32_t g = (uint32_t)(tt * GP_NCHUNK + c);
+            const int sb = tt & 1;
+            float4 xv[N];
+#pragma unroll
+            for (int n = 0; n < N; ++n) xv[n] = xn[n];
             {
-                GP_T0();
-                gp_wait_warp(&s_full[sb], (t >> 1) & 1, 8 + sb);
-                GP_ACC(0);
+                const float* xp = I + GP_PROD_WARPS < total_items ? item_ptr(I + GP_PROD_WARPS) : nullptr;
+#pragma unroll
+                for (int n = 0; n < N; ++n)
+                    xn[n] = (xp && !(a.ablate & 4)) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            const float* Ssm = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes);
-            for (int c = 0; c < GP_NCHUNK; ++c, ++g) {
-                const int slot = g & 1;
-                // before storing into a unit of group g: the MMAs of group g - 2 (same slot) must have completed
-                const uint32_t free_inst = (((g - 2) >> 1) & 3) * 2 * GP_MAX_K, free_parity = ((g - 2) >> 3) & 1;
-                unsigned char* abase = sm + L.a_off + (size_t)slot * K * L.a_unit;
-                int kdone = 0;                      // taps of this group this warp has already signalled
-                for (int j = 0; j < ipg; ++j) {
-                    if ((item_base + (uint32_t)(c * ipg + j)) % GP_PROD_WARPS != (uint32_t)warp) continue;
-                    const long long t_item0 = TIMING ? clock64() : 0;
-                    const int sl = j * 4 + ql;
-                    constexpr bool kAllInTile = (TS % 4) == 0;
-                    const bool in_tile = kAllInTile || sl < TS;
-                    const bool sv = sl < ns;
-                    float4 xv[N];
-                    const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + c * 32 + l8 * 4;
-#pragma unroll
-                    for (int n = 0; n < N; ++n)
-                        xv[n] = sv ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
-#pragma unroll
-                    for (int n = 0; n < N; ++n) {
-                        xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
-                    }
-                    const float* Ss = Ssm + (size_t)(in_tile ? sl : 0) * N * NP;
-                    uint32_t ahi[N];
-                    gp_row_addrs<N>(smem_u32(abase), sl * N, l8, ahi);
-                    const bool last_item = true;    // (ipg <= GP_PROD_WARPS: a warp has at most one item per group)
-                    // taps one after the other, loop NOT unrolled: one copy of the propagation + split/store code (the
-                    // fully unrolled item was 27 KB of SASS; with the epilogue it thrashed the 32 KB instruction cache)
-#pragma unroll 1
-                    for (int k = 0; k < K; ++k) {
-                        if (k > 0) {
-                            float4 z[N];
-                            gp_propagate<N>(Ss, xv, z);
-#pragma unroll
-                            for (int n = 0; n < N; ++n) xv[n] = z[n];
-                        }
-                        const int u = slot * GP_MAX_K + k;
-                        if (g >= 2 && kdone <= k) {
-                            GP_T0();
-                            gp_wait_warp(&a_free[free_inst + u], free_parity, 6 + u);
-                            GP_ACC(1);
-                        }
-                        if (in_tile) gp_store_tap<N>(ahi, xv);
-#pragma unroll
-                        for (int n = 0; n < N; ++n) ahi[n] += L.a_unit;
-                        if (last_item) {
-                            fence_proxy_async_smem();       // st.shared operand rows -> visible to the tensor cores
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(&a_full[u], 0);
-                            kdone = k + 1;
-                        }
-                    }
-                    if (TIMING) {
-                        tm[2] += (unsigned long long)(clock64() - t_item0);
-                        tm[3] += 1;
-                    }
+            if (tt != cur_tile) {
+                if (cur_tile >= 0) {                   // done with the S buffer of the previous tile
+                    __syncwarp();
+                    if (lane == 0) gp_arrive(&s_free[cur_tile & 1]);
                 }
-                // Warps without an item in the group do not touch its barriers: an arrival for group g+2 cannot land in
-                // group g's phase of the same unit, because the arriving warp first waited for a_free of that unit, i.e.
-                // for MMAs that were only issued once group g's phase had completed.
+                GP_T0();
+                gp_wait_warp(&s_full[sb], (tt >> 1) & 1, 8 + sb);
+                GP_ACC(0);
+                cur_tile = tt;
             }
+            const int smp = (2 * (cluster_id + tt * num_clusters) + (int)rank) * TS + sl;
+            const float scale = smp < a.B ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
+            }
+            if (g >= 2) {       // the MMAs of group g - 2 (same ring slot) must have completed
+                GP_T0();
+                gp_wait_warp(&a_free[(((g - 2) >> 1) & 3) * 2 + slot], ((g - 2) >> 3) & 1, 2 + slot);
+                GP_ACC(1);
+            }
+            const bool st_ok = !(a.ablate & 2);
+            if (st_ok) gp_store_rows<N, 0, N>(ahi0, 0u, xv);
+            const float* Ms = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes) + (size_t)sl * N * NP;
+            uint32_t tap_off = L.a_unit;
+            // taps 1 (x.S) and 2 (x.(S.S)): the loop is NOT unrolled -- one copy of the propagation + split/store
+            // code (fully unrolled, the item was 27 KB of SASS and thrashed the instruction cache)
+#pragma unroll 1
+            for (int k = 1; k < K; ++k) {
+                if (a.ablate & 1) break;
+                {
+                    float4 zh[NA];
+                    gp_propagate_half<N, 0, NA, 0>(Ms, xv, zh);
+                    if (st_ok) gp_store_rows<N, 0, NA>(ahi0, tap_off, zh);
+                }
+                if (NB > 0) {
+                    float4 zh[NB > 0 ? NB : 1];
+                    gp_propagate_half<N, NA, (NB > 0 ? NB : 1), SLOT_B>(Ms, xv, zh);
+                    if (st_ok) gp_store_rows<N, NA, (NB > 0 ? NB : 1)>(ahi0, tap_off, zh);
+                }
+                Ms += (size_t)TS * N * NP;          // S.S follows S in the buffer
+                tap_off += L.a_unit;
+            }
+            fence_proxy_async_smem();       // st.shared operand rows -> visible to the tensor cores
             __syncwarp();
-            if (lane == 0) gp_arrive(&s_free[sb]);
-            item_base += (uint32_t)(GP_NCHUNK * ipg);
+            if (lane == 0) mbar_arrive_cluster(&a_full[slot], 0);
+            if (TIMING) {
+                tm[2] += (unsigned long long)(clock64() - t_item0);
+                tm[3] += 1;
+            }
+        }
+        if (cur_tile >= 0) {
+            __syncwarp();
+            if (lane == 0) gp_arrive(&s_free[cur_tile & 1]);
         }
         if (TIMING && a.timing && lane == 0 && warp == 0) {
             atomicAdd(&a.timing[0], tm[0]); atomicAdd(&a.timing[1], tm[1]); atomicAdd(&a.timing[2], tm[2]);
@@ -748,6 +788,7 @@ int launch_gf_forward_pair(const float* x, const void* S, int s_is_f64, const vo
     a.num_pairs = (a.num_tiles + 1) / 2;
     a.s_is_f64 = s_is_f64; a.relu = relu; a.has_act = wa_host ? 1 : 0;
     a.tail_rows = (TS * N) % 32;
+    a.ablate = debug_option(DBG_PAIR_ABLATE);
     a.timing = nullptr;
     if (debug_option(DBG_TC_TIMING)) {
         if (!g_pair_timing) {

@@ -265,7 +265,7 @@ extern "C" int gpp_debug_feature_timing(unsigned long long* out7) { return debug
 // debug switches (include/gnnpp_b200_debug.h)
 extern "C" int gpp_debug_set_option(const char* name, int value) {
     GPP_REQUIRE(name, GPP_ERR_INVALID, "debug_set_option: null name");
-    static const char* const names[DBG_COUNT] = {"gf_timing", "tc_timing", "fe_timing", "no_pdl", "gf_mode"};
+    static const char* const names[DBG_COUNT] = {"gf_timing", "tc_timing", "fe_timing", "no_pdl", "gf_mode", "pair_ablate"};
     for (int i = 0; i < DBG_COUNT; ++i)
         if (strcmp(name, names[i]) == 0) {
             g_debug_options[i] = value;

@@ -14,7 +14,10 @@ extern "C" {
  *   "gf_timing" / "tc_timing" / "fe_timing"  != 0: the CUDA-core filter / tcgen05 kernels / CUDA-core feature
  *                 kernel accumulate per-phase clock64() totals, read with the gpp_debug_*_timing calls below
  *   "no_pdl"     != 0: planner kernels are launched without programmatic dependent launch
- *   "gf_mode"    kernel choice of the standalone gpp_graph_filter_forward: 0 auto, 1 CUDA-core, 2 tcgen05 */
+ *   "gf_mode"    kernel choice of the standalone gpp_graph_filter_forward: 0 auto, 1 CUDA-core, 2 tcgen05 3xTF32,
+ *                3 tcgen05 CTA-pair fp16-split
+ *   "pair_ablate" (performance experiments only, results are wrong) bit mask for the CTA-pair kernel: 1 skip the
+ *                propagations, 2 skip the operand stores, 4 skip the x loads, 8 skip the y stores */
 int gpp_debug_set_option(const char* name, int value);
 
 /* Test hook for the tcgen05 plumbing: D[128][128] = A[128][32] . B[128][32]^T on the tensor cores
