@@ -23,9 +23,9 @@
 //     (TMEM -> registers -> scale, bias, ReLU -> swizzled staging -> TMA tensor store / 128->5 logits) overlaps the
 //     MMAs of tile i+1 and the propagation of tile i+2.
 //
-// Warp roles (512 threads per CTA): 0-5 producers (x -> z_k -> fp16 hi|lo operand rows), 6 MMA issuer (one lane; leader
-// CTA only) + TMEM allocation + tap load, 8-11 epilogue (one TMEM lane quarter each), 7 and 12-15 scouts (S and S.S
-// staging, scales).
+// Warp roles (640 threads per CTA): 0-11 producers (x -> z_k -> fp16 hi|lo operand rows), 12-15 epilogue (one TMEM lane
+// quarter each), 16 MMA issuer (one lane; leader CTA only) + TMEM allocation + tap load, 17-19 scouts (S and S.S
+// staging, scales, L2 prefetch).
 // Operand row layout: 128 bytes = [32 x hi | 32 x lo] fp16 of one (tap, 32-feature chunk), SWIZZLE_128B K-major; the
 // three products of a K = 16 step differ only in the descriptors' start offsets (+0 / +64 bytes).
 #include "common.cuh"
@@ -36,11 +36,12 @@
 
 namespace gpp {
 
-constexpr int GP_THREADS = 512;
-constexpr int GP_PROD_WARPS = 6;            // warps 0..5: exactly the 2 ring groups x 3 items that can be in flight
-constexpr int GP_MMA_WARP = 6;
-constexpr int GP_EPI_WARP0 = 8;             // warps 8..11: (warp % 4) = TMEM lane quarter
-constexpr int GP_SCOUT_WARPS = 5;           // warps 7, 12..15
+constexpr int GP_THREADS = 640;
+constexpr int GP_PROD_WARPS = 12;           // warps 0..11: 2 ring groups x 3 sample quads x 2 item kinds
+constexpr int GP_EPI_WARP0 = 12;            // warps 12..15: (warp % 4) = TMEM lane quarter
+constexpr int GP_MMA_WARP = 16;
+constexpr int GP_SCOUT_WARP0 = 17;          // warps 17..19
+constexpr int GP_SCOUT_WARPS = 3;
 constexpr int GP_M = 128;                   // node rows per CTA tile
 constexpr int GP_C = 128;                   // G = F
 constexpr int GP_NCHUNK = 4;                // 32-feature chunks
@@ -251,7 +252,7 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 2 * ((TS + 3) / 4));      // the item warps of the group, both CTAs
+            mbar_init(&a_full[i], GP_PROD_WARPS);            // the 6 item warps of the group, both CTAs
             for (int q4 = 0; q4 < 4; ++q4) mbar_init(&a_free[q4 * 2 + i], 1);
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_free[i], 2 * 4);
@@ -273,8 +274,7 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const bool is_scout = warp == 7 || warp >= 12;
-    if (warp == GP_MMA_WARP || is_scout) {
+    if (warp >= GP_MMA_WARP) {
       if (warp == GP_MMA_WARP) {
         // =========================== tap load + MMA issuer ===========================
         if (lane == 0) {
@@ -334,10 +334,10 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         __syncwarp();
       } else {
         // =========================== scouts: S staging + per-sample scales, one tile ahead ===========================
-        // Five warps, each owning every fifth sample of the tile -- one warp doing all 12 samples in turn was the critical
-        // path of the whole kernel (33 K cycles per tile, profiles/r02_pair_phase_v1.txt), three warps with one sample
-        // in flight still took 7 us per tile (profiles/r02_pair_ablation_v10.txt: "pipeline skeleton").
-        const int sw = warp == 7 ? 0 : warp - 11;      // scout index 0..4
+        // Three warps, each owning every third sample of the tile -- one warp doing all 12 samples in turn was the critical
+        // path of the whole kernel (33 K cycles per tile, profiles/r02_pair_phase_v1.txt); their loads hit L2 thanks to
+        // the bulk prefetch issued two tiles earlier.
+        const int sw = warp - GP_SCOUT_WARP0;
         int t = 0;
         for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
             const int tile = 2 * p + (int)rank;
@@ -350,94 +350,98 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 GP_ACC(0);
             }
             const long long t_work0 = TIMING ? clock64() : 0;
+            if (sw == 0 && lane == 0) {
+                // pull the x rows and GSOs of the tile after next into L2: this role's own loads then wait for L2, not for
+                // HBM (the pipeline skeleton alone took 5.6 us per tile waiting for them, profiles/r02_pair_phase_v11.txt)
+                const int tile2 = 2 * (p + 2 * num_clusters) + (int)rank;
+                const long long first = (long long)tile2 * TS;
+                if (first < a.B) {
+                    const long long cnt = min((long long)TS, (long long)a.B - first);
+                    const uint32_t xb = (uint32_t)(cnt * N * GP_C * 4);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.x + first * N * GP_C), "r"(xb) : "memory");
+                    const size_t ssz = a.s_is_f64 ? 8 : 4;
+                    const uint32_t sbytes = (uint32_t)((cnt * N * N * ssz) & ~(size_t)15);
+                    const char* sp = reinterpret_cast<const char*>(a.S) + (size_t)first * N * N * ssz;
+                    if (sbytes && (reinterpret_cast<uintptr_t>(sp) & 15u) == 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sp), "r"(sbytes) : "memory");
+                }
+            }
             float* Sd = reinterpret_cast<float*>(sm + L.s_off + sb * L.s_bytes);
-            for (int sl0 = sw; sl0 < TS; sl0 += 2 * GP_SCOUT_WARPS) {
-                // two samples (2 x (10 + 4) loads per lane) in flight: this role is latency-bound -- one DRAM round trip
-                // per batch of loads -- and, one tile ahead of everything else, it paces the whole pipeline
-                float4 xv[2][N];
-                float se[2][4];
+            for (int sl = sw; sl < TS; sl += GP_SCOUT_WARPS) {      // one sample (10 + 4 loads per lane) in flight per warp
+                const bool v = sl < ns;
+                float4 xv[N];
+                float se[4];
+                const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int sl = sl0 + h * GP_SCOUT_WARPS;
-                    const bool v = sl < ns;
-                    const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
+                for (int n = 0; n < N; ++n)
+                    xv[n] = v ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const size_t so = (size_t)(s0 + sl) * N * N;
 #pragma unroll
-                    for (int n = 0; n < N; ++n)
-                        xv[h][n] = v ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const size_t so = (size_t)(s0 + sl) * N * N;
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * lane + i;
+                    const bool ve = v && e < N * N;
+                    se[i] = !ve ? 0.f
+                                : (a.s_is_f64 ? static_cast<float>(reinterpret_cast<const double*>(a.S)[so + e])   // S.float(), graphML.py:2350
+                                              : reinterpret_cast<const float*>(a.S)[so + e]);
+                }
+                if (v) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int e = 4 * lane + i;
-                        const bool ve = v && e < N * N;
-                        se[h][i] = !ve ? 0.f
-                                       : (a.s_is_f64 ? static_cast<float>(reinterpret_cast<const double*>(a.S)[so + e])   // S.float(), graphML.py:2350
-                                                     : reinterpret_cast<const float*>(a.S)[so + e]);
+                        if (e < N * N) Sd[(sl * N + e / N) * NP + gp_slot(N, e % N)] = se[i];
                     }
                 }
+                __syncwarp();
+                float e2 = 1.f, e2inv = 1.f;
+                if (v) {
+                    // largest |x| of the sample
+                    float mx = 0.f;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int sl = sl0 + h * GP_SCOUT_WARPS;
-                    if (sl >= TS) continue;
-                    const bool v = sl < ns;
-                    if (v) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = 4 * lane + i;
-                            if (e < N * N) Sd[(sl * N + e / N) * NP + gp_slot(N, e % N)] = se[h][i];
-                        }
+                    for (int n = 0; n < N; ++n) {
+                        const float4 q4 = xv[n];
+                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
                     }
-                    __syncwarp();
-                    float e2 = 1.f, e2inv = 1.f;
-                    if (v) {
-                        // largest |x| of the sample (the read above is also the L2 prefetch of the tile for the producers)
-                        float mx = 0.f;
+                    // largest absolute column sum of S: |z_k[n]| <= max|z_{k-1}| * sum_m |S[m][n]|
+                    float cs = 0.f;
+                    if (lane < N) {
 #pragma unroll
-                        for (int n = 0; n < N; ++n) {
-                            const float4 q4 = xv[h][n];
-                            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
-                        }
-                        // largest absolute column sum of S: |z_k[n]| <= max|z_{k-1}| * sum_m |S[m][n]|
-                        float cs = 0.f;
-                        if (lane < N) {
-#pragma unroll
-                            for (int m = 0; m < N; ++m) cs += fabsf(Sd[(sl * N + m) * NP + gp_slot(N, lane)]);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                            cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, o));
-                        }
-                        float bound = mx;
-                        const float cm = fmaxf(cs, 1.f);
-                        for (int k = 1; k < K; ++k) bound *= cm;
-                        // bound in [2^q, 2^(q+1)): scale by 2^(14-q) so that every |z_k| * scale < 2^15 (fp16 max 65504)
-                        const uint32_t bits = __float_as_uint(bound);
-                        const int q = (int)((bits >> 23) & 0xFF) - 127;
-                        if (bound > 0.f && q < 128) {
-                            int e = 14 - q;
-                            e = max(-100, min(100, e));
-                            e2 = __uint_as_float((uint32_t)(e + 127) << 23);
-                            e2inv = __uint_as_float((uint32_t)(127 - e) << 23);
-                        }
+                        for (int m = 0; m < N; ++m) cs += fabsf(Sd[(sl * N + m) * NP + gp_slot(N, lane)]);
                     }
-                    if (lane == 0) {
-                        scale_p[sb * GP_MAX_TS + sl] = e2;
-                        scale_e[(t & (GP_SCALE_RING - 1)) * GP_MAX_TS + sl] = e2inv;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, o));
                     }
-                    if (K > 2 && v) {
-                        // S.S for the third tap: z_2 = (x.S).S = x.(S.S), so the producers form every tap straight from x
-                        float* S2d = Sd + TS * N * NP;
+                    float bound = mx;
+                    const float cm = fmaxf(cs, 1.f);
+                    for (int k = 1; k < K; ++k) bound *= cm;
+                    // bound in [2^q, 2^(q+1)): scale by 2^(14-q) so that every |z_k| * scale < 2^15 (fp16 max 65504)
+                    const uint32_t bits = __float_as_uint(bound);
+                    const int q = (int)((bits >> 23) & 0xFF) - 127;
+                    if (bound > 0.f && q < 128) {
+                        int e = 14 - q;
+                        e = max(-100, min(100, e));
+                        e2 = __uint_as_float((uint32_t)(e + 127) << 23);
+                        e2inv = __uint_as_float((uint32_t)(127 - e) << 23);
+                    }
+                }
+                if (lane == 0) {
+                    scale_p[sb * GP_MAX_TS + sl] = e2;
+                    scale_e[(t & (GP_SCALE_RING - 1)) * GP_MAX_TS + sl] = e2inv;
+                }
+                if (K > 2 && v) {
+                    // S.S for the third tap: z_2 = (x.S).S = x.(S.S), so the producers form every tap straight from x
+                    float* S2d = Sd + TS * N * NP;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = 4 * lane + i;
-                            if (e < N * N) {
-                                const int m = e / N, n = e % N;
-                                float acc = 0.f;
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = 4 * lane + i;
+                        if (e < N * N) {
+                            const int m = e / N, n = e % N;
+                            float acc = 0.f;
 #pragma unroll
-                                for (int jj = 0; jj < N; ++jj)
-                                    acc = fmaf(Sd[(sl * N + m) * NP + gp_slot(N, jj)], Sd[(sl * N + jj) * NP + gp_slot(N, n)], acc);
-                                S2d[(sl * N + m) * NP + gp_slot(N, n)] = acc;
-                            }
+                            for (int jj = 0; jj < N; ++jj)
+                                acc = fmaf(Sd[(sl * N + m) * NP + gp_slot(N, jj)], Sd[(sl * N + jj) * NP + gp_slot(N, n)], acc);
+                            S2d[(sl * N + m) * NP + gp_slot(N, n)] = acc;
                         }
                     }
                 }
@@ -549,52 +553,41 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         // nodes of sample ql.  Every tap is formed straight from x (z_1 = x.S, z_2 = x.(S.S)), one half of the output
         // nodes at a time, so the live state is x (N x 4) + half a tap ((N+2)/2 x 4) + N row addresses.
         constexpr int NA = gp_na(N), NB = N - NA, SLOT_B = gp_slot_b(N);
-        constexpr int ipg = (TS + 3) >> 2;             // items per group
+        constexpr int nquad = (TS + 3) >> 2;           // sample quads per tile
+        constexpr int ipg = 2 * nquad;                 // items per group: (quad, kind)
         constexpr int ipt = ipg * GP_NCHUNK;           // items per tile
         static_assert(2 * ipg == GP_PROD_WARPS, "producer warps = the items of the two ring groups");
         static_assert((TS % 4) == 0, "item = 4 whole samples");
-        // Item I (global sequence of this CTA) = (tile I / ipt, chunk (I % ipt) / ipg, sample quad (I % ipt) % ipg); warp w
-        // takes I = w, w + 6, ...: its quad is w % 3 and its groups all have parity w / 3, i.e. ONE ring slot for good.
-        // What bounds the kernel is the latency of one item (a slot is busy from the first operand store until the MMAs
-        // that read it have completed), so the x rows of the NEXT item are fetched into registers while this one runs.
+        // An item = (tile, 32-feature chunk, quad of 4 samples, kind): kind 0 stores tap 0 (x) and tap 1 (x.S), kind 1
+        // stores tap 2 (x.(S.S)) -- every tap comes straight from x, so the two kinds are independent and run on two
+        // warps (what bounds the ring is the LATENCY of an item: a slot is busy from the first operand store until the
+        // MMAs that read it have completed).  Warp w always works on ring slot w / 6, quad (w % 6) % 3, kind (w % 6) / 3;
+        // its items are I = w, w + 12, ... of the CTA's sequence (tile I / 24, chunk (I % 24) / 6).
         const int ql = lane >> 3;
         const int l8 = lane & 7;
-        const int jq = warp % ipg;
         const int slot = warp / ipg;
-        const int sl = jq * 4 + ql;                    // sample of the tile this lane works for, in every item
+        const int kind = (warp % ipg) / nquad;
+        const int sl = ((warp % ipg) % nquad) * 4 + ql;     // sample of the tile this lane works for, in every item
         int ntile_seq = 0;
         for (int p = cluster_id; p < a.num_pairs; p += num_clusters) ++ntile_seq;
         const int total_items = ntile_seq * ipt;
         uint32_t ahi0[N];                              // operand row addresses of tap 0 (same rows, same slot every item)
         gp_row_addrs<N>(smem_u32(sm + L.a_off + (size_t)slot * K * L.a_unit), sl * N, l8, ahi0);
-        auto item_ptr = [&](int I) -> const float* {
-            const int tt = I / ipt, c = (I - tt * ipt) / ipg;
-            const int tile = 2 * (cluster_id + tt * num_clusters) + (int)rank;
-            const int smp = tile * TS + sl;
-            return smp < a.B ? a.x + ((size_t)smp * N) * GP_C + c * 32 + l8 * 4 : nullptr;
-        };
-        float4 xn[N];
-        {
-            const float* xp = warp < total_items ? item_ptr(warp) : nullptr;
-#pragma unroll
-            for (int n = 0; n < N; ++n)
-                xn[n] = (xp && !(a.ablate & 4)) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        const bool has_work = kind == 0 || K > 2;      // (K < 3: the kind-1 warps only keep the barrier counts)
+        const bool st_ok = !(a.ablate & 2);
         int cur_tile = -1;
         for (int I = warp; I < total_items; I += GP_PROD_WARPS) {
             const long long t_item0 = TIMING ? clock64() : 0;
             const int tt = I / ipt, c = (I - tt * ipt) / ipg;
             const uint32_t g = (uint32_t)(tt * GP_NCHUNK + c);
             const int sb = tt & 1;
+            const int smp = (2 * (cluster_id + tt * num_clusters) + (int)rank) * TS + sl;
+            const bool sv = smp < a.B && has_work && !(a.ablate & 4);
             float4 xv[N];
+            const float* xp = a.x + ((size_t)smp * N) * GP_C + c * 32 + l8 * 4;
 #pragma unroll
-            for (int n = 0; n < N; ++n) xv[n] = xn[n];
-            {
-                const float* xp = I + GP_PROD_WARPS < total_items ? item_ptr(I + GP_PROD_WARPS) : nullptr;
-#pragma unroll
-                for (int n = 0; n < N; ++n)
-                    xn[n] = (xp && !(a.ablate & 4)) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int n = 0; n < N; ++n)
+                xv[n] = sv ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)n * GP_C)) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (tt != cur_tile) {
                 if (cur_tile >= 0) {                   // done with the S buffer of the previous tile
                     __syncwarp();
@@ -605,26 +598,24 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 GP_ACC(0);
                 cur_tile = tt;
             }
-            const int smp = (2 * (cluster_id + tt * num_clusters) + (int)rank) * TS + sl;
-            const float scale = smp < a.B ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
+            const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
 #pragma unroll
             for (int n = 0; n < N; ++n) {
                 xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
             }
+            const float* Ms = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes) + (size_t)sl * N * NP;
             if (g >= 2) {       // the MMAs of group g - 2 (same ring slot) must have completed
                 GP_T0();
                 gp_wait_warp(&a_free[(((g - 2) >> 1) & 3) * 2 + slot], ((g - 2) >> 3) & 1, 2 + slot);
                 GP_ACC(1);
             }
-            const bool st_ok = !(a.ablate & 2);
-            if (st_ok) gp_store_rows<N, 0, N>(ahi0, 0u, xv);
-            const float* Ms = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes) + (size_t)sl * N * NP;
-            uint32_t tap_off = L.a_unit;
-            // taps 1 (x.S) and 2 (x.(S.S)): the loop is NOT unrolled -- one copy of the propagation + split/store
-            // code (fully unrolled, the item was 27 KB of SASS and thrashed the instruction cache)
-#pragma unroll 1
-            for (int k = 1; k < K; ++k) {
-                if (a.ablate & 1) break;
+            if (kind == 0) {
+                if (st_ok) gp_store_rows<N, 0, N>(ahi0, 0u, xv);
+            } else {
+                Ms += (size_t)TS * N * NP;          // S.S follows S in the buffer
+            }
+            if (has_work && (kind == 1 || K > 1) && !(a.ablate & 1)) {
+                const uint32_t tap_off = (kind == 0 ? 1u : 2u) * L.a_unit;
                 {
                     float4 zh[NA];
                     gp_propagate_half<N, 0, NA, 0>(Ms, xv, zh);
@@ -635,8 +626,6 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                     gp_propagate_half<N, NA, (NB > 0 ? NB : 1), SLOT_B>(Ms, xv, zh);
                     if (st_ok) gp_store_rows<N, NA, (NB > 0 ? NB : 1)>(ahi0, tap_off, zh);
                 }
-                Ms += (size_t)TS * N * NP;          // S.S follows S in the buffer
-                tap_off += L.a_unit;
             }
             fence_proxy_async_smem();       // st.shared operand rows -> visible to the tensor cores
             __syncwarp();
