@@ -167,8 +167,6 @@ template <int N, int N0, int CNT, int SLOT0>
 __device__ __forceinline__ void gp_propagate_half(const float* __restrict__ Ms, const float4 (&in)[N], float4 (&out)[CNT]) {
     constexpr int NP = gp_np(N);
 #pragma unroll
-    for (int i = 0; i < CNT; ++i) out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
     for (int m = 0; m < N; ++m) {
         float sv[(CNT + 3) & ~3];
 #pragma unroll
@@ -183,10 +181,17 @@ __device__ __forceinline__ void gp_propagate_half(const float* __restrict__ Ms, 
         }
 #pragma unroll
         for (int i = 0; i < CNT; ++i) {
-            out[i].x = fmaf(sv[i], in[m].x, out[i].x);
-            out[i].y = fmaf(sv[i], in[m].y, out[i].y);
-            out[i].z = fmaf(sv[i], in[m].z, out[i].z);
-            out[i].w = fmaf(sv[i], in[m].w, out[i].w);
+            if (m == 0) {        // first term: no accumulator to clear
+                out[i].x = sv[i] * in[m].x;
+                out[i].y = sv[i] * in[m].y;
+                out[i].z = sv[i] * in[m].z;
+                out[i].w = sv[i] * in[m].w;
+            } else {
+                out[i].x = fmaf(sv[i], in[m].x, out[i].x);
+                out[i].y = fmaf(sv[i], in[m].y, out[i].y);
+                out[i].z = fmaf(sv[i], in[m].z, out[i].z);
+                out[i].w = fmaf(sv[i], in[m].w, out[i].w);
+            }
         }
     }
 }
@@ -367,10 +372,13 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 }
             }
             float* Sd = reinterpret_cast<float*>(sm + L.s_off + sb * L.s_bytes);
-            for (int sl = sw; sl < TS; sl += GP_SCOUT_WARPS) {      // one sample (10 + 4 loads per lane) in flight per warp
+            // Software pipeline over this warp's samples: the loads of sample k+1 are issued as soon as the registers of
+            // sample k are free (after its |x| fold and the S store), so their latency overlaps the column sums, the
+            // scale and the S.S product of sample k.
+            float4 xv[N];
+            float se[4];
+            auto issue_loads = [&](int sl) {
                 const bool v = sl < ns;
-                float4 xv[N];
-                float se[4];
                 const float* xp = a.x + ((size_t)(s0 + sl) * N) * GP_C + lane * 4;
 #pragma unroll
                 for (int n = 0; n < N; ++n)
@@ -384,23 +392,28 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                                 : (a.s_is_f64 ? static_cast<float>(reinterpret_cast<const double*>(a.S)[so + e])   // S.float(), graphML.py:2350
                                               : reinterpret_cast<const float*>(a.S)[so + e]);
                 }
+            };
+            if (sw < TS) issue_loads(sw);
+            for (int sl = sw; sl < TS; sl += GP_SCOUT_WARPS) {
+                const bool v = sl < ns;
+                float mx = 0.f;
                 if (v) {
+                    // largest |x| of the sample
+#pragma unroll
+                    for (int n = 0; n < N; ++n) {
+                        const float4 q4 = xv[n];
+                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
+                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int e = 4 * lane + i;
                         if (e < N * N) Sd[(sl * N + e / N) * NP + gp_slot(N, e % N)] = se[i];
                     }
                 }
+                if (sl + GP_SCOUT_WARPS < TS) issue_loads(sl + GP_SCOUT_WARPS);
                 __syncwarp();
                 float e2 = 1.f, e2inv = 1.f;
                 if (v) {
-                    // largest |x| of the sample
-                    float mx = 0.f;
-#pragma unroll
-                    for (int n = 0; n < N; ++n) {
-                        const float4 q4 = xv[n];
-                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(q4.x), fabsf(q4.y)), fmaxf(fabsf(q4.z), fabsf(q4.w))));
-                    }
                     // largest absolute column sum of S: |z_k[n]| <= max|z_{k-1}| * sum_m |S[m][n]|
                     float cs = 0.f;
                     if (lane < N) {
@@ -441,7 +454,7 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
 #pragma unroll
                             for (int jj = 0; jj < N; ++jj)
                                 acc = fmaf(Sd[(sl * N + m) * NP + gp_slot(N, jj)], Sd[(sl * N + jj) * NP + gp_slot(N, n)], acc);
-                            S2d[(sl * N + m) * NP + gp_slot(N, n)] = acc;
+                            S2d[(sl * N + m) * NP + gp_slot(N, n)] = acc * e2;      // carries the sample's scale: tap-2 items use x as it is
                         }
                     }
                 }
@@ -598,10 +611,12 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 GP_ACC(0);
                 cur_tile = tt;
             }
-            const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
+            if (kind == 0) {        // (the staged S.S already carries the scale)
+                const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
 #pragma unroll
-            for (int n = 0; n < N; ++n) {
-                xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
+                for (int n = 0; n < N; ++n) {
+                    xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
+                }
             }
             const float* Ms = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes) + (size_t)sl * N * NP;
             if (g >= 2) {       // the MMAs of group g - 2 (same ring slot) must have completed
