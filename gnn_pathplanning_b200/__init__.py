@@ -11,9 +11,9 @@ dotted names (`graphs.models.decentralplanner`, `utils.graphUtils.graphML`,
 """
 from . import _lib
 from .graphml import BatchLSIGF, GraphFilterBatch, graph_filter, FEATURE_MAJOR, NODE_MAJOR
-from .planner import DecentralPlannerNet, weights_init
+from .planner import DecentralPlannerNet, planner_loss, weights_init
 
-__all__ = ["DecentralPlannerNet", "GraphFilterBatch", "BatchLSIGF", "graph_filter", "weights_init",
+__all__ = ["DecentralPlannerNet", "GraphFilterBatch", "BatchLSIGF", "graph_filter", "weights_init", "planner_loss",
            "FEATURE_MAJOR", "NODE_MAJOR", "install_dropin", "build"]
 
 

@@ -37,7 +37,7 @@ EXPORTED = (
     "gpp_graph_filter_backward_workspace_bytes", "gpp_graph_filter_backward",
     "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
     "gpp_planner_forward", "gpp_planner_forward_host",
-    "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward",
+    "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward", "gpp_planner_ce_loss",
     "gpp_planner_forward_host_async", "gpp_planner_wait",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
     "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode",
@@ -175,6 +175,8 @@ def load():
         lib.gpp_planner_train_backward.restype = i
         lib.gpp_planner_train_backward.argtypes = [C.POINTER(PlannerWeights), vp, vp, i, vp, vp,
                                                    C.POINTER(PlannerGrads), i, i, i, vp]
+        lib.gpp_planner_ce_loss.restype = i
+        lib.gpp_planner_ce_loss.argtypes = [vp, vp, i, vp, vp, C.c_float, i, i, vp]
         lib.gpp_planner_forward_host_async.restype = i
         lib.gpp_planner_forward_host_async.argtypes = [vp, vp, vp, i, vp, i, i, C.POINTER(C.c_ulonglong)]
         lib.gpp_planner_wait.restype = i

@@ -867,6 +867,73 @@ extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const fl
     return GPP_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused training loss: replaces the per-agent loop of
+// agents/decentralplannerlocal.py:305-312 -- loss = (1/N) sum_i CrossEntropy(predict[i], argmax(target[:, i])) -- and
+// the backward seed d loss / d logits, in ONE launch on the contiguous [N,B,5] logits (the reference's loop is N
+// log-softmax + NLL + mean kernels forward and as many backward).  One block, fp64 partial sums combined in a fixed
+// order: deterministic.  argmax = first maximum, as torch.max(., 1)[1] on a one-hot row.
+// ---------------------------------------------------------------------------------------
+namespace gpp {
+template <typename T>
+__global__ void __launch_bounds__(1024) ce_loss_kernel(const float* __restrict__ logits, const T* __restrict__ target,
+                                                       float* __restrict__ loss, float* __restrict__ dlogits, int B, int N,
+                                                       float grad_scale) {
+    __shared__ double red[32];
+    const int rows = N * B;
+    const float inv = 1.f / (float)rows;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        const int n = r / B, b = r - n * B;
+        const float* lp = logits + (size_t)r * 5;
+        const T* tp = target + ((size_t)b * N + n) * 5;            // target is [B,N,5]
+        int cls = 0;
+        T best = tp[0];
+#pragma unroll
+        for (int q = 1; q < 5; ++q)
+            if (tp[q] > best) { best = tp[q]; cls = q; }
+        float v[5], mx = lp[0];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { v[q] = lp[q]; mx = fmaxf(mx, v[q]); }
+        float sum = 0.f, e[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) { e[q] = expf(v[q] - mx); sum += e[q]; }
+        const float lse = mx + logf(sum);
+        acc += (double)(lse - v[cls]);
+        if (dlogits) {
+            const float rs = 1.f / sum;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) dlogits[(size_t)r * 5 + q] = (e[q] * rs - (q == cls ? 1.f : 0.f)) * inv * grad_scale;
+        }
+    }
+    // fixed-order reduction: lanes by xor-butterfly (same tree every run), warps in index order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) t += red[wv];
+        *loss = (float)(t / (double)rows);
+    }
+}
+}  // namespace gpp
+
+extern "C" int gpp_planner_ce_loss(const float* logits, const void* target_onehot, int target_is_i64, float* loss,
+                                   float* dlogits, float grad_scale, int B, int N, void* stream) {
+    GPP_REQUIRE(logits && target_onehot && loss, GPP_ERR_INVALID, "planner_ce_loss: null pointer");
+    GPP_REQUIRE(B >= 1 && N >= 1, GPP_ERR_INVALID, "planner_ce_loss: bad sizes B=%d N=%d", B, N);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (target_is_i64)
+        ce_loss_kernel<long long><<<1, 1024, 0, st>>>(logits, reinterpret_cast<const long long*>(target_onehot), loss, dlogits,
+                                                      B, N, grad_scale);
+    else
+        ce_loss_kernel<float><<<1, 1024, 0, st>>>(logits, reinterpret_cast<const float*>(target_onehot), loss, dlogits, B, N,
+                                                  grad_scale);
+    GPP_LAUNCH_CHECK();
+    return GPP_OK;
+}
+
 // debug: single training kernels for unit tests (tests/ only)
 //   op 0: conv3x3_fwd (a = in, b = w, c = bias)      op 1: conv3x3_bwd_input (a = dz, b = w)
 //   op 2: maxpool2_bwd (a = act, b = dp)           op 3: conv3x3 weight/bias gradient (a = dz, b = in) -> dW | db

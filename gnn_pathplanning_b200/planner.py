@@ -118,6 +118,52 @@ class _PlannerTrainFn(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+class _FusedCELossFn(torch.autograd.Function):
+    """loss = (1/N) sum_i CE(logits[i], argmax target[:, i]) and its gradient in one launch (gpp_planner_ce_loss)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        lib = _lib.load()
+        N, B = logits.shape[0], logits.shape[1]
+        lg = logits.contiguous()
+        tg = target.contiguous()
+        loss = torch.empty(1, device=lg.device, dtype=torch.float32)
+        dl = torch.empty_like(lg) if logits.requires_grad else None
+        with torch.cuda.device(lg.device):
+            _lib.check(lib.gpp_planner_ce_loss(lg.data_ptr(), tg.data_ptr(), int(tg.dtype == torch.int64), loss.data_ptr(),
+                                               dl.data_ptr() if dl is not None else None, 1.0, B, N,
+                                               torch.cuda.current_stream(lg.device).cuda_stream))
+        ctx.save_for_backward(dl)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g if dl is not None else None), None
+
+
+def planner_loss(logits, target_onehot):
+    """The reference's training loss (agents/decentralplannerlocal.py:293,305-312) as ONE fused kernel.
+
+    logits: the [N,B,5] tensor of `DecentralPlannerNet.forward_logits`, or the list of N [B,5] tensors `forward`
+    returns (views of one buffer); target_onehot: [B,N,5] int64 / float32 one-hot expert actions.  Differentiable in
+    the logits.  CUDA only."""
+    if isinstance(logits, (list, tuple)):
+        base = getattr(logits[0], "_base", None)
+        if (base is not None and base.dim() == 3 and base.shape[0] == len(logits)
+                and all(getattr(t, "_base", None) is base for t in logits)):
+            logits = base                    # the list forward() returned: N views of one [N,B,5] buffer
+        else:
+            logits = torch.stack(list(logits))
+    _require_cuda(logits, "logits")
+    _require_cuda(target_onehot, "target")
+    if target_onehot.dtype not in (torch.int64, torch.float32):
+        target_onehot = target_onehot.float()
+    assert logits.dim() == 3 and logits.shape[2] == 5 and logits.dtype == torch.float32
+    assert tuple(target_onehot.shape) == (logits.shape[1], logits.shape[0], 5)
+    return _FusedCELossFn.apply(logits, target_onehot)
+
+
 def _fill_weights(params, module):
     """params in _train_params() order -> gpp_planner_weights (running stats from the module's buffers)."""
     w = _lib.PlannerWeights()
@@ -212,6 +258,10 @@ class DecentralPlannerNet(nn.Module):
         self.S = S.unsqueeze(1)
 
     def forward(self, inputTensor) -> List[torch.Tensor]:
+        return list(self.forward_logits(inputTensor).unbind(0))
+
+    def forward_logits(self, inputTensor) -> torch.Tensor:
+        """Same computation as `forward`, returned as the one [N,B,5] tensor the list is made of (agent-major)."""
         _require_cuda(inputTensor, "inputTensor")
         assert inputTensor.dim() == 5 and tuple(inputTensor.shape[2:]) == (3, 11, 11)
         assert self.S is not None, "addGSO(S) must be called before forward"
@@ -233,7 +283,7 @@ class DecentralPlannerNet(nn.Module):
             raise NotImplementedError(
                 "gnn_pathplanning_b200: eval-mode forward with autograd enabled is not supported; wrap inference "
                 "in torch.no_grad() or switch the module to train() for a differentiable forward")
-        return list(logits.unbind(0))
+        return logits
 
     def _train_params(self):
         convs = [self.ConvLayers[ci] for ci in _CONV_IDX]

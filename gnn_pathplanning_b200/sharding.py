@@ -80,15 +80,13 @@ def train_step(model, optimizer, bucket: Optional[GradientBucket], x, S, target_
     """One sharded training step with the reference's loss (agents/decentralplannerlocal.py
     :297-317): mean over agents of CrossEntropy(logits_i, argmax target_i), then ONE gradient
     all-reduce, then the optimizer step.  Returns the local (shard) loss."""
-    import torch.nn.functional as Fn
+    from .planner import planner_loss
     if bucket is not None:
         bucket.zero()
     else:
         optimizer.zero_grad(set_to_none=False)
     model.addGSO(S)
-    logits: List[torch.Tensor] = model(x)
-    cls = target_onehot.permute(1, 0, 2).argmax(-1)
-    loss = sum(Fn.cross_entropy(logits[i], cls[i]) for i in range(len(logits))) / len(logits)
+    loss = planner_loss(model.forward_logits(x), target_onehot)      # one fused loss + gradient-seed kernel
     loss.backward()
     if bucket is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
         bucket.all_reduce(x.shape[0], global_batch, group=group)

@@ -183,6 +183,14 @@ int gpp_planner_train_backward(const gpp_planner_weights* w, const float* x, con
                                const float* dlogits, void* workspace, const gpp_planner_grads* g,
                                int B, int N, int K, void* stream);
 
+/* Fused training loss (replaces the per-agent loop of agents/decentralplannerlocal.py:305-312 and its autograd graph):
+ *   loss = (1/N) sum_i CrossEntropy(logits[i], argmax_a target[:, i, a])          (mean over the batch per agent)
+ *   dlogits[i,b,:] = grad_scale * (softmax(logits[i,b,:]) - onehot) / (N*B)       (NULL to skip)
+ *   logits dev f32 [N,B,5] (as gpp_planner_forward / _train_forward write them); target_onehot dev [B,N,5], int64
+ *   (target_is_i64 != 0, the dataloader's format) or f32; loss dev f32 [1].  One launch, deterministic. */
+int gpp_planner_ce_loss(const float* logits, const void* target_onehot, int target_is_i64, float* loss,
+                        float* dlogits, float grad_scale, int B, int N, void* stream);
+
 /* Asynchronous variant for pipelined rollouts over independent episode batches: enqueues the same
  * zero-copy forward on the planner's stream and returns at once with a completion ticket; the host
  * buffers MUST be pinned and must stay untouched until gpp_planner_wait(ticket) returns.  Calls are

@@ -315,3 +315,54 @@ def test_optimizer_steps_follow_oracle():
         got = torch.stack(m(xt.cuda())).cpu().numpy()
         ref = torch.stack(po.planner_forward(own, St, xt)).numpy()
     assert rel_err(got, ref) <= TOL
+
+
+@pytest.mark.parametrize("N,B,dtype", [(10, 64, torch.int64), (20, 64, torch.float32), (3, 1, torch.int64), (40, 300, torch.int64)])
+def test_fused_training_loss(N, B, dtype):
+    """gpp_planner_ce_loss (row f3) against the reference's per-agent loop (agents/decentralplannerlocal.py:305-312,
+    restated in oracle/planner_oracle.py: planner_loss) -- value and gradient, both target dtypes, and taken from the
+    list-of-views `forward` returns as well as from the [N,B,5] tensor."""
+    import gnn_pathplanning_b200 as gp
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    g = torch.Generator().manual_seed(N * 100 + B)
+    logits = (torch.randn(N, B, 5, generator=g) * 3.0)
+    tgt = torch.from_numpy(synthetic.random_targets(B, N, seed=N + B)).to(dtype)
+    ref_in = logits.clone().double().requires_grad_(True)
+    ref = po.planner_loss(list(ref_in.unbind(0)), tgt)
+    ref.backward()
+    lc = logits.cuda().requires_grad_(True)
+    loss = gp.planner_loss(lc, tgt.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * max(1.0, abs(ref.item()))
+    assert rel_err(lc.grad.cpu().numpy(), ref_in.grad.numpy()) <= 1e-6
+    lc2 = logits.cuda().requires_grad_(True)
+    views = list((lc2 * 1.0).unbind(0))                 # N views of one buffer, as DecentralPlannerNet.forward returns
+    loss2 = gp.planner_loss(views, tgt.cuda())
+    loss2.backward()
+    assert loss2.item() == loss.item() and torch.equal(lc2.grad, lc.grad)
+    (gp.planner_loss(lc2.detach(), tgt.cuda()))          # no-grad path
+
+
+def test_train_step_with_fused_loss_matches_per_agent_loss(golden):
+    g = golden("planner_K3.npz")
+    import gnn_pathplanning_b200 as gp
+    from oracle import planner_oracle as po
+    N, K = int(g["N"]), int(g["K"])
+    x = torch.from_numpy(g["x"].astype(np.float32)).cuda()
+    S = torch.from_numpy(g["S"]).float().cuda()
+    tgt = torch.from_numpy(g["target"].astype(np.int64)).cuda()
+    grads = []
+    for fused in (False, True):
+        m = _model(_sd(g), N, K).train()
+        m.addGSO(S)
+        if fused:
+            loss = gp.planner_loss(m.forward_logits(x), tgt)
+        else:
+            loss = po.planner_loss(m(x), tgt)
+        loss.backward()
+        assert abs(loss.item() - float(g["train_loss"])) <= 1e-5 * max(1.0, abs(float(g["train_loss"])))
+        grads.append({n_: p.grad.clone() for n_, p in m.named_parameters()})
+    for n_ in grads[0]:
+        assert rel_err(grads[1][n_].cpu().numpy(), grads[0][n_].cpu().numpy()) <= 1e-5 or \
+            float((grads[1][n_] - grads[0][n_]).abs().max()) <= 1e-6, n_
