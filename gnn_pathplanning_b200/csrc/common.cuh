@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/gnnpp_b200.h"
@@ -11,7 +12,7 @@ namespace gpp {
 
 // ---- error plumbing -------------------------------------------------------------------
 void set_error(const char* fmt, ...);
-extern thread_local unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 
 #define GPP_CUDA_OK(expr)                                                                  \
     do {                                                                                   \

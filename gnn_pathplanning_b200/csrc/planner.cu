@@ -18,7 +18,7 @@ namespace gpp {
 
 // ---- error / bookkeeping ----------------------------------------------------------------
 static thread_local char g_err[512] = "";
-thread_local unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};     // process-wide: autograd runs the backward on its own thread
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -170,8 +170,8 @@ struct gpp_planner {
 
 extern "C" const char* gpp_last_error(void) { return gpp::g_err; }
 extern "C" int gpp_abi_version(void) { return 1; }
-extern "C" unsigned long long gpp_launch_count(void) { return gpp::g_launches; }
-extern "C" void gpp_reset_launch_count(void) { gpp::g_launches = 0; }
+extern "C" unsigned long long gpp_launch_count(void) { return gpp::g_launches.load(); }
+extern "C" void gpp_reset_launch_count(void) { gpp::g_launches.store(0); }
 
 extern "C" int gpp_device_info(int* sms, int* cc_major, int* cc_minor) {
     int dev = 0;

@@ -218,7 +218,7 @@ int gpp_planner_set_feature_mode(gpp_planner* p, int mode);
 int gpp_planner_set_profiling(gpp_planner* p, int enable);
 int gpp_planner_get_profile(gpp_planner* p, double* feature_ms, double* graph_filter_ms, int* steps);
 
-/* Number of kernels of this library launched by the calling thread's planner calls since
+/* Number of kernels of this library launched by this process (any thread) since
  * the last reset (bench.py's gpu_launches claim is read from here, not guessed). */
 unsigned long long gpp_launch_count(void);
 void gpp_reset_launch_count(void);
