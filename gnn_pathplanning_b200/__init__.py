@@ -10,10 +10,11 @@ dotted names (`graphs.models.decentralplanner`, `utils.graphUtils.graphML`,
 `graphs.weights_initializer`) resolve to this package.
 """
 from . import _lib
-from .graphml import BatchLSIGF, GraphFilterBatch, graph_filter, FEATURE_MAJOR, NODE_MAJOR
+from .graphml import (BatchLSIGF, GraphFilterBatch, GraphFilterL2ShareBatch, GraphFilterMoRNNBatch, GraphFilterRNNBatch,
+                      graph_filter, torchpermul, FEATURE_MAJOR, NODE_MAJOR)
 from .planner import DecentralPlannerNet, planner_loss, weights_init
 
-__all__ = ["DecentralPlannerNet", "GraphFilterBatch", "BatchLSIGF", "graph_filter", "weights_init", "planner_loss",
+__all__ = ["DecentralPlannerNet", "GraphFilterBatch", "BatchLSIGF", "graph_filter", "weights_init", "planner_loss", "GraphFilterRNNBatch", "GraphFilterMoRNNBatch", "GraphFilterL2ShareBatch", "torchpermul",
            "FEATURE_MAJOR", "NODE_MAJOR", "install_dropin", "build"]
 
 

@@ -183,3 +183,115 @@ class GraphFilterBatch(nn.Module):
         s = "in_features=%d, out_features=%d, filter_taps=%d, edge_features=%d, bias=%s, " % (
             self.G, self.F, self.K, self.E, self.bias is not None)
         return s + ("GSO stored" if self.S is not None else "no GSO stored")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Recurrent layers on the same primitive: every BatchLSIGF call is the fused kernel,
+# the hidden-state glue (add, ReLU, the element-wise `torchpermul`) is point-wise.
+# ---------------------------------------------------------------------------------------------------------
+def torchpermul(h, x, b=None):
+    """Same contract as the reference's torchpermul (graphML.py:2656-2679): the ELEMENT-WISE product
+    y[b,g,n] = x[b,g,n] * h[g,n] (+ b) -- defined only when the node count equals h.shape[0]."""
+    y = torch.mul(x.permute(0, 2, 1), h.permute(1, 0)).permute(0, 2, 1)
+    if b is not None:
+        y = y + b
+    return y
+
+
+class _GraphFilterRecurrentBase(nn.Module):
+    """Shared surface of GraphFilterRNNBatch / GraphFilterMoRNNBatch / GraphFilterL2ShareBatch
+    (graphML.py:2491-2987): parameters weight_A/B/D + bias_A/B/D, addGSO, updateHiddenState, forward."""
+
+    _graph_hidden = True          # weight_B / weight_D are graph filters ([*,E,K,H]); else plain [*,H] matrices
+
+    def __init__(self, G, H, F, K, E=1, bias=True):
+        super().__init__()
+        self.G = G
+        self.F = F
+        self.H = H
+        self.K = K
+        self.E = E
+        self.S = None
+        self.weight_A = nn.parameter.Parameter(torch.Tensor(H, E, K, G))
+        if self._graph_hidden:
+            self.weight_B = nn.parameter.Parameter(torch.Tensor(H, E, K, H))
+            self.weight_D = nn.parameter.Parameter(torch.Tensor(F, E, K, H))
+        else:
+            self.weight_B = nn.parameter.Parameter(torch.Tensor(H, H))
+            self.weight_D = nn.parameter.Parameter(torch.Tensor(F, H))
+        if bias:
+            self.bias_A = nn.parameter.Parameter(torch.Tensor(H, 1))
+            self.bias_B = nn.parameter.Parameter(torch.Tensor(H, 1))
+            self.bias_D = nn.parameter.Parameter(torch.Tensor(F, 1))
+        else:
+            # (as in the reference, :2564-2565: only `bias` is registered, so reset_parameters below raises
+            # AttributeError on bias_A -- the reference cannot be built with bias=False either)
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv_a = 1. / math.sqrt(self.G * self.K)
+        self.weight_A.data.uniform_(-stdv_a, stdv_a)
+        if self.bias_A is not None:
+            self.bias_A.data.uniform_(-stdv_a, stdv_a)
+        stdv_b = 1. / math.sqrt(self.H * self.K) if self._graph_hidden else 1. / math.sqrt(self.H)
+        self.weight_B.data.uniform_(-stdv_b, stdv_b)
+        if self.bias_B is not None:
+            self.bias_B.data.uniform_(-stdv_b, stdv_b)
+        self.weight_D.data.uniform_(-stdv_b, stdv_b)
+        if self.bias_D is not None:
+            self.bias_D.data.uniform_(-stdv_b, stdv_b)
+
+    def addGSO(self, S):
+        assert len(S.shape) == 4
+        assert S.shape[1] == self.E
+        self.N = S.shape[2]
+        assert S.shape[3] == self.N
+        self.S = S
+
+    def updateHiddenState(self, hiddenState):
+        self.hiddenState = hiddenState
+
+    def forward(self, x):
+        B, _, Nin = x.shape
+        if Nin < self.N:
+            x = torch.cat((x, torch.zeros(B, x.shape[1], self.N - Nin, dtype=x.dtype, device=x.device)), dim=2)
+        u_a = BatchLSIGF(self.weight_A, self.S, x, self.bias_A)
+        if self._graph_hidden:
+            u_b = BatchLSIGF(self.weight_B, self.S, self.hiddenState, self.bias_B)
+        else:
+            u_b = torchpermul(self.weight_B, self.hiddenState, self.bias_B)
+        self.hiddenStateNext = torch.relu_(u_a + u_b)
+        if self._graph_hidden:
+            u = BatchLSIGF(self.weight_D, self.S, self.hiddenStateNext, self.bias_D)
+        else:
+            u = torchpermul(self.weight_D, self.hiddenStateNext, self.bias_D)
+        self.updateHiddenState(self.hiddenStateNext)
+        if Nin < self.N:
+            u = u[:, :, :Nin]
+        return u
+
+    def extra_repr(self):
+        s = "in_features=%d, out_features=%d, hidden_features=%d, filter_taps=%d, edge_features=%d, bias=%s, " % (
+            self.G, self.F, self.H, self.K, self.E, self.bias_D is not None)
+        return s + ("GSO stored" if self.S is not None else "no GSO stored")
+
+
+class GraphFilterRNNBatch(_GraphFilterRecurrentBase):
+    """GraphFilterRNNBatch(G, H, F, K, E=1, bias=True) -- graphML.py:2491-2654: hidden' = ReLU(A(S) x + B(S) hidden),
+    y = D(S) hidden', with A, B, D K-tap graph filters; `detachHiddenState` as :2606-2612."""
+
+    def detachHiddenState(self):
+        self.hiddenState.detach_()
+        self.hiddenStateNext.detach_()
+
+
+class GraphFilterMoRNNBatch(_GraphFilterRecurrentBase):
+    """GraphFilterMoRNNBatch -- graphML.py:2681-2834: hidden' = ReLU(A(S) x + torchpermul(B, hidden)),
+    y = torchpermul(D, hidden')."""
+    _graph_hidden = False
+
+
+class GraphFilterL2ShareBatch(_GraphFilterRecurrentBase):
+    """GraphFilterL2ShareBatch -- graphML.py:2837-2987 (same arithmetic as the MoRNN variant)."""
+    _graph_hidden = False

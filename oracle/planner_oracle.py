@@ -120,6 +120,43 @@ def graph_filter_f64(weight, bias, S, x) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------
+# Recurrent graph-filter layers built on the same primitive
+# ----------------------------------------------------------------------------
+def torchpermul(h: torch.Tensor, x: torch.Tensor, b: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Restates torchpermul (graphML.py:2656-2679): an ELEMENT-WISE product with broadcasting,
+    y[b,g,n] = x[b,g,n] * h[g,n] -- only defined when the node count equals h.shape[0] (the reference's
+    `torch.mul(x.permute(0,2,1), h.permute(1,0))`)."""
+    y = torch.mul(x.permute(0, 2, 1), h.permute(1, 0)).permute(0, 2, 1)      # :2672
+    if b is not None:
+        y = y + b                                                            # :2675-2676
+    return y
+
+
+def graph_filter_rnn_step(kind: str, p: Dict[str, torch.Tensor], S4: torch.Tensor, x: torch.Tensor,
+                          hidden: torch.Tensor):
+    """One forward of GraphFilterRNNBatch (kind "rnn", graphML.py:2617-2641), GraphFilterMoRNNBatch ("mornn",
+    :2791-2812) or GraphFilterL2ShareBatch ("l2share", :2947-2968); p holds weight_A/B/D, bias_A/B/D.
+    Returns (u, hiddenStateNext)."""
+    N = S4.shape[2]
+    B, _, Nin = x.shape
+    if Nin < N:
+        x = torch.cat((x, torch.zeros(B, x.shape[1], N - Nin, dtype=x.dtype)), dim=2)
+    u_a = batch_lsigf(p["weight_A"], S4, x, p["bias_A"])
+    if kind == "rnn":
+        u_b = batch_lsigf(p["weight_B"], S4, hidden, p["bias_B"])
+    else:
+        u_b = torchpermul(p["weight_B"], hidden, p["bias_B"])
+    nxt = torch.relu(u_a + u_b)
+    if kind == "rnn":
+        u = batch_lsigf(p["weight_D"], S4, nxt, p["bias_D"])
+    else:
+        u = torchpermul(p["weight_D"], nxt, p["bias_D"])
+    if Nin < N:
+        u = u[:, :, :Nin]
+    return u, nxt
+
+
+# ----------------------------------------------------------------------------
 # Whole planner forward
 # ----------------------------------------------------------------------------
 def _cnn_one_agent(sd: Dict[str, torch.Tensor], xi: torch.Tensor, training: bool,

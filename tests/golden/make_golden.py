@@ -5,6 +5,7 @@ Run in the build container only:   python tests/golden/make_golden.py
 Outputs (float32 unless noted), all consumed by tests/test_oracle_golden.py (CPU,
 pins the oracle) and tests/test_gpu_parity.py (GPU, pins the CUDA path):
 
+  rnn_cases.npz       GraphFilterRNNBatch / GraphFilterMoRNNBatch / GraphFilterL2ShareBatch, two recurrent steps
   gf_cases.npz        GraphFilterBatch / BatchLSIGF: hand-derivable KATs
                       + random cases incl. float64 GSO, Nin < N zero-padding, K=1,
                       the alternate reference path batchLSIGF(matrixPowersBatch)
@@ -99,6 +100,51 @@ def gf_cases(gml):
     return out
 
 
+def rnn_cases(gml):
+    """GraphFilterRNNBatch / GraphFilterMoRNNBatch / GraphFilterL2ShareBatch (graphML.py:2491-2987): two time steps
+    each (hidden state carried over), outputs + hidden states + input gradients.  The Mo / L2Share variants combine
+    the hidden state through `torchpermul` (:2656-2679), an ELEMENT-WISE product that only broadcasts when
+    nodes == hidden == output features -- the cases respect that."""
+    out = {}
+    g = torch.Generator().manual_seed(424242)
+    cases = [  # name, class, B, N, G, H, F, K
+        ("rnn_128", "GraphFilterRNNBatch", 3, 10, 128, 128, 128, 3),
+        ("rnn_small", "GraphFilterRNNBatch", 2, 7, 6, 10, 4, 2),
+        ("mornn", "GraphFilterMoRNNBatch", 2, 12, 20, 12, 12, 3),
+        ("l2share", "GraphFilterL2ShareBatch", 3, 9, 128, 9, 9, 2),
+    ]
+    names = []
+    for name, cls, B, N, G, H, F, K in cases:
+        layer = getattr(gml, cls)(G, H, F, K, 1, True)
+        with torch.no_grad():
+            for p_ in layer.parameters():
+                p_.copy_((torch.rand(p_.shape, generator=g) - 0.5) * 0.4)
+        S = torch.from_numpy(np.stack([synthetic.gso_from_positions(
+            np.random.default_rng(17 + i).integers(0, 10, size=(N, 2)), 5.0) for i in range(B)])).float()
+        layer.addGSO(S.unsqueeze(1))
+        h0 = torch.randn(B, H, N, generator=g) * 0.5
+        layer.updateHiddenState(h0.clone())
+        xs = [torch.randn(B, G, N, generator=g) for _ in range(2)]
+        xg = [x.clone().requires_grad_(True) for x in xs]
+        ys, hs = [], []
+        for t in range(2):
+            y = layer(xg[t])
+            ys.append(y)
+            hs.append(layer.hiddenState.clone())
+        gy = torch.randn(ys[1].shape, generator=g)
+        (ys[1] * gy).sum().backward()
+        out.update({name + "_S": S.numpy(), name + "_h0": h0.numpy(), name + "_x0": xs[0].numpy(), name + "_x1": xs[1].numpy(),
+                    name + "_y0": ys[0].detach().numpy(), name + "_y1": ys[1].detach().numpy(),
+                    name + "_h1": hs[0].detach().numpy(), name + "_h2": hs[1].detach().numpy(),
+                    name + "_gy": gy.numpy(), name + "_gx0": xg[0].grad.numpy(), name + "_gx1": xg[1].grad.numpy(),
+                    name + "_gwA": layer.weight_A.grad.numpy(), name + "_cfg": np.array([B, N, G, H, F, K])})
+        for pn, pv in layer.named_parameters():
+            out[name + "_p_" + pn] = pv.detach().numpy()
+        names.append(name + ":" + cls)
+    out["names"] = np.array(names)
+    return out
+
+
 def planner_case(dcp, K, N, B, map_w, f64_gso, seed=1337):
     torch.manual_seed(seed)                      # main.py:71-72 seeds torch before building the net
     m = dcp.DecentralPlannerNet(ref_shim.Config(N, K))
@@ -164,6 +210,7 @@ def main():
     gml, dcp, st = ref_shim.load()
     sim = ref_shim.load_sim()
     np.savez_compressed(os.path.join(HERE, "gf_cases.npz"), **gf_cases(gml))
+    np.savez_compressed(os.path.join(HERE, "rnn_cases.npz"), **rnn_cases(gml))
     np.savez_compressed(os.path.join(HERE, "planner_K3.npz"), **planner_case(dcp, 3, 10, 4, 20, False))
     np.savez_compressed(os.path.join(HERE, "planner_K2.npz"), **planner_case(dcp, 2, 10, 1, 20, True))
     np.savez_compressed(os.path.join(HERE, "inputs.npz"), **input_cases(st, sim))

@@ -154,3 +154,34 @@ def test_properties_at_full_size():
     perm = torch.randperm(N, generator=gen).cuda()
     yp = g.graph_filter(x1[:, :, perm].contiguous(), S[:, perm][:, :, perm].contiguous(), w, b)
     assert rel_err(yp.cpu().numpy(), f(x1, b)[:, :, perm].cpu().numpy()) <= TOL
+
+
+def test_recurrent_layers_vs_golden(golden):
+    """Row f4: GraphFilterRNNBatch / GraphFilterMoRNNBatch / GraphFilterL2ShareBatch on the fused filter kernels,
+    two recurrent steps against the reference's own modules (tests/golden/rnn_cases.npz): outputs, hidden states,
+    input and tap gradients through both steps."""
+    import gnn_pathplanning_b200 as g
+    gold = golden("rnn_cases.npz")
+    for entry in gold["names"]:
+        name, cls = str(entry).split(":")
+        B, N, G, H, F, K = [int(v) for v in gold[name + "_cfg"]]
+        layer = getattr(g, cls)(G, H, F, K, 1, True)
+        with torch.no_grad():
+            for pn, pv in layer.named_parameters():
+                pv.copy_(torch.from_numpy(gold[name + "_p_" + pn]))
+        layer = layer.cuda()
+        layer.addGSO(torch.from_numpy(gold[name + "_S"]).unsqueeze(1).cuda())
+        layer.updateHiddenState(torch.from_numpy(gold[name + "_h0"]).cuda())
+        xs = [torch.from_numpy(gold["%s_x%d" % (name, t)]).cuda().requires_grad_(True) for t in range(2)]
+        ys = []
+        for t in range(2):
+            y = layer(xs[t])
+            ys.append(y)
+            assert rel_err(y.detach().cpu().numpy(), gold["%s_y%d" % (name, t)]) <= TOL, (name, t)
+            assert rel_err(layer.hiddenState.detach().cpu().numpy(), gold["%s_h%d" % (name, t + 1)]) <= TOL, (name, t)
+        (ys[1] * torch.from_numpy(gold[name + "_gy"]).cuda()).sum().backward()
+        assert rel_err(xs[0].grad.cpu().numpy(), gold[name + "_gx0"]) <= 5e-5, name
+        assert rel_err(xs[1].grad.cpu().numpy(), gold[name + "_gx1"]) <= 5e-5, name
+        assert rel_err(layer.weight_A.grad.cpu().numpy(), gold[name + "_gwA"]) <= 5e-5, name
+    with pytest.raises(AttributeError):
+        g.GraphFilterRNNBatch(4, 4, 4, 2, 1, False)          # as the reference: bias=False cannot be constructed
