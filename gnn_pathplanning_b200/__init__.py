@@ -13,8 +13,9 @@ from . import _lib
 from .graphml import (BatchLSIGF, GraphFilterBatch, GraphFilterL2ShareBatch, GraphFilterMoRNNBatch, GraphFilterRNNBatch,
                       graph_filter, torchpermul, FEATURE_MAJOR, NODE_MAJOR)
 from .planner import DecentralPlannerNet, planner_loss, weights_init
+from .rollout import BatchedRollout
 
-__all__ = ["DecentralPlannerNet", "GraphFilterBatch", "BatchLSIGF", "graph_filter", "weights_init", "planner_loss", "GraphFilterRNNBatch", "GraphFilterMoRNNBatch", "GraphFilterL2ShareBatch", "torchpermul",
+__all__ = ["DecentralPlannerNet", "GraphFilterBatch", "BatchLSIGF", "graph_filter", "weights_init", "planner_loss", "BatchedRollout", "GraphFilterRNNBatch", "GraphFilterMoRNNBatch", "GraphFilterL2ShareBatch", "torchpermul",
            "FEATURE_MAJOR", "NODE_MAJOR", "install_dropin", "build"]
 
 

@@ -14,7 +14,7 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgnnpp_b200.so")
-SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "graph_filter_pair.cu", "feature.cu", "feature_tc.cu", "train.cu", "planner.cu")
+SOURCES = ("graph_filter.cu", "graph_filter_tc.cu", "graph_filter_pair.cu", "rollout.cu", "feature.cu", "feature_tc.cu", "train.cu", "planner.cu")
 HEADERS = ("common.cuh", "feature.cuh", "tc_common.cuh")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200.h")
 INCLUDE_DEBUG = os.path.join(os.path.dirname(PKG_DIR), "include", "gnnpp_b200_debug.h")
@@ -37,7 +37,7 @@ EXPORTED = (
     "gpp_graph_filter_backward_workspace_bytes", "gpp_graph_filter_backward",
     "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
     "gpp_planner_forward", "gpp_planner_forward_host",
-    "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward", "gpp_planner_ce_loss",
+    "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward", "gpp_planner_ce_loss", "gpp_rollout_build_inputs", "gpp_rollout_move",
     "gpp_planner_forward_host_async", "gpp_planner_wait",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
     "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode",
@@ -177,6 +177,10 @@ def load():
                                                    C.POINTER(PlannerGrads), i, i, i, vp]
         lib.gpp_planner_ce_loss.restype = i
         lib.gpp_planner_ce_loss.argtypes = [vp, vp, i, vp, vp, C.c_float, i, i, vp]
+        lib.gpp_rollout_build_inputs.restype = i
+        lib.gpp_rollout_build_inputs.argtypes = [vp, vp, vp, i, vp, i, vp, vp, i, vp, i, i, i, vp]
+        lib.gpp_rollout_move.restype = i
+        lib.gpp_rollout_move.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, vp]
         lib.gpp_planner_forward_host_async.restype = i
         lib.gpp_planner_forward_host_async.argtypes = [vp, vp, vp, i, vp, i, i, C.POINTER(C.c_ulonglong)]
         lib.gpp_planner_wait.restype = i

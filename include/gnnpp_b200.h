@@ -191,6 +191,38 @@ int gpp_planner_train_backward(const gpp_planner_weights* w, const float* x, con
 int gpp_planner_ce_loss(const float* logits, const void* target_onehot, int target_is_i64, float* loss,
                         float* dlogits, float grad_scale, int B, int N, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * GPU-resident rollout step, B episodes in lock-step (what surrounds the forward in the reference's
+ * rollout loop, agents/decentralplannerlocal.py:560-592; the reference runs it on the host, one episode
+ * at a time).  All pointers are device pointers; positions are integer cells (x, y) and never leave the
+ * device between steps.
+ *
+ * gpp_rollout_build_inputs replaces multiRobotSim.getCurrentState (utils/multirobotsim_dcenlocal.py:425-453
+ * -> AgentState.toInputTensor, dataloader/statetransformer.py:82-130) and multiRobotSim.getGSO (:367-394 ->
+ * computeAdjacencyMatrix :320-365, connectivity test graphTools.py:396-423):
+ *   pos, goal  [B,N,2] int32      map [B,W,W] or (map_shared) [W,W] uint8, 1 = obstacle
+ *   radius     [B] f64 in/out: communication radius.  grow_radius != 0 (the reference's step 0): radius is divided by
+ *              1.1 once, then multiplied by 1.1 until the graph is connected, and written back.
+ *   x          out f32 [B,N,3,11,11]   S out [B,N,N] f64 (s_is_f64, as the simulator emits) or f32
+ *   connected  out [B] int32 or NULL
+ * Bit-exact with the reference (integer window arithmetic; the GSO is IEEE float64 sqrt / divide / multiply).
+ *
+ * gpp_rollout_move replaces multiRobotSim.move (:562-723) incl. interRobotCollision (:462-555):
+ *   logits [N,B,5] (as the planner writes them); action = first maximum (LogSoftmax + argmax, :589-591); moves into
+ *   the map edge or an obstacle become "stay"; vertex conflicts and position swaps are resolved as the reference does.
+ *   Where the reference draws random.choice(collided agents), the contract here is round-robin: the c-th draw of the
+ *   episode picks collided[c % len] (agent order); c is choice_counter[b].
+ *   pos in/out; reached / start_step / end_step [B,N] in/out (-1 = not yet); last_action [B,N] out; maxstep [B];
+ *   active [B] or NULL (0 = leave the episode untouched); flags [B,3] out = {all agents had reached their goal before
+ *   this move, check_moveCollision, check_predictCollsion}; currentstep = 1-based step index (:561). */
+int gpp_rollout_build_inputs(const int* pos, const int* goal, const unsigned char* map, int map_shared,
+                             double* radius, int grow_radius, float* x, void* S, int s_is_f64,
+                             int* connected, int B, int N, int W, void* stream);
+int gpp_rollout_move(const float* logits, int* pos, const int* goal, const unsigned char* map, int map_shared,
+                     const int* maxstep, const int* active, int* reached, int* start_step, int* end_step,
+                     int* last_action, unsigned int* choice_counter, int* flags, int currentstep, int B, int N,
+                     int W, void* stream);
+
 /* Asynchronous variant for pipelined rollouts over independent episode batches: enqueues the same
  * zero-copy forward on the planner's stream and returns at once with a completion ticket; the host
  * buffers MUST be pinned and must stay untouched until gpp_planner_wait(ticket) returns.  Calls are
