@@ -429,6 +429,53 @@ def leg_inference(gp, timer, dev, rank, world, n, k, batch, map_w, gso_dtype, K,
     return out
 
 
+def leg_rollout(gp, timer, dev, rank, world, n, k, episodes, map_w, K, warmup, label, cpu):
+    """Rows f1/f2: one lock-step rollout step of `episodes` device-resident episodes = gpp_rollout_build_inputs (FOV tensors
+    + float64 GSOs from the positions) -> planner forward -> gpp_rollout_move; nothing crosses PCIe.  The CPU figure next to
+    it is the oracle's restatement of the reference simulator's per-step work around the model (getCurrentState + getGSO +
+    move, one episode at a time, oracle/sim_oracle.py)."""
+    from gnn_pathplanning_b200 import synthetic
+    rng = np.random.default_rng(77 + rank)
+    cases = [synthetic.random_episode(rng, n, map_w, 0.1) for _ in range(min(episodes, 64))]
+    rep = (episodes + len(cases) - 1) // len(cases)
+    maps = np.stack([c[0] for c in cases] * rep)[:episodes]
+    starts = np.stack([c[1] for c in cases] * rep)[:episodes]
+    goals = np.stack([c[2] for c in cases] * rep)[:episodes]
+    sd = make_state_dict(k, seed=1000 + n)
+    sd["actionsMLP.0.weight"] = sd["actionsMLP.0.weight"] * 40.0
+    model = build_model(gp, sd, n, k, dev)
+    ro = gp.BatchedRollout(n, 6.0, dev).setup(starts, goals, maps, 1 << 30)
+
+    def step(i):
+        x, S = ro.build_inputs(i + 1)
+        model.addGSO(S)
+        ro.move(model.forward_logits(x), i + 2)
+    with torch.no_grad():
+        from gnn_pathplanning_b200 import _lib
+        l0 = _lib.launch_count()
+        step(0)
+        launches = _lib.launch_count() - l0
+        ms, R = timer.device_windows(step, K, warmup)
+    (ms,) = timer.max_over_ranks(ms)
+    out = {"workload": label, "us_per_step": 1e3 * ms / K, "episode_steps_per_s": world * episodes * K / (ms * 1e-3),
+           "agent_steps_per_s": world * episodes * n * K / (ms * 1e-3), "windows": R, "launches_per_step": int(launches),
+           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if cpu:
+        from oracle import sim_oracle
+        sim = sim_oracle.SimOracle(n, 6.0).setup(starts[0], goals[0], maps[0], 1 << 30)
+        lg = np.random.default_rng(5).standard_normal((200, n, 5)).astype(np.float32)
+        t0, cnt = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 2.0:
+            sim.inputs(cnt + 1)
+            sim.move(lg[cnt % 200], cnt + 2)
+            cnt += 1
+        out["cpu_sim_us_per_episode_step"] = 1e6 * (time.perf_counter() - t0) / cnt
+        out["cpu_sim_note"] = "oracle/sim_oracle.py, one episode, 1 thread, simulator work only (no model), %d steps" % cnt
+    del model, ro
+    torch.cuda.empty_cache()
+    return out
+
+
 def leg_training(gp, timer, dist, dev, rank, world, n, batch, map_w, K, warmup, label):
     """forward (train-mode, per-agent BatchNorm) + fused cross-entropy + backward + [flat gradient all-reduce] + Adam."""
     from gnn_pathplanning_b200 import sharding, synthetic, _lib
@@ -633,6 +680,9 @@ def main():
                                                "DCP K=2, 10 agents, 20x20 map, batch=1 (configs[0]): rollout-step latency, float64 GSO")
             legs["C4"] = leg_inference(gp, timer, dev, rank, world, 40, 3, 256, 50, np.float32, max(5, K // 4), W, args.pool_mb,
                                        "DCP K=3, 40 agents, 50x50 map, batch=256 inference per GPU (configs[3])")
+            legs["rollout_C2"] = leg_rollout(gp, timer, dev, rank, world, 10, 3, 256, 20, max(5, K // 4), W,
+                                             "256 device-resident episodes per GPU in lock-step (10 agents, 20x20 map, K=3): "
+                                             "inputs builder + planner forward + move per step", rank == 0 and world == 1)
         tk = max(5, K // 10)
         if world == 1:
             legs["train_C3"] = leg_training(gp, timer, dist, dev, rank, world, 10, 64, 20, tk, 3,

@@ -1,0 +1,794 @@
+// im2col-free tensor-core feature extractor for sm_100a: the per-agent CNN + compress MLP of DecentralPlannerNet
+// (/root/reference/graphs/models/decentralplanner.py:155-195,284-290, eval mode) on tcgen05 with fp16 2-way split
+// operands (fp32 parity), 8 agents per tile, one persistent CTA per SM.
+//
+// Layout idea.  An activation map lives in shared memory as fp16 (hi | lo) planes of 8 channels, one 16-byte vector per
+// padded pixel, pixels in ONE linear order over the whole tile:   row = y * (8 agents * Wp) + agent * Wp + x.
+// That is exactly the canonical NO-SWIZZLE K-major UMMA operand layout (rows 16 B apart, 8-row groups 128 B apart,
+// K planes `rows * 16` B apart), and in it the 3x3 tap (ky, kx) of EVERY output pixel is the same buffer shifted by
+// (ky * 8 * Wp + kx) rows: the A operand of a tap is just the descriptor start address moved by a multiple of 16 B
+// (profiles/probes/umma_nosw_probe.cu checks this addressing on the hardware).  No im2col copy exists anywhere: an
+// epilogue writes a layer's output once, and the next layer's 9 taps x Cin/16 MMAs read it in place.  With the
+// y-major order the rows a layer needs (y < Hout) are a prefix, so M covers needed image rows only.
+//
+//   layer  in grid (Hp x Wp)  rows   planes  out ch  M tiles  taps x k16   B bytes
+//   conv0  13 x 16 (11+pad)   1664   1       32      10       3 x 2 (*)    12 KB   (*) two ky taps per K=16: LBO = one row
+//   conv1  7 x 7              392    4       32      3        9 x 2        36 KB
+//   conv2  7 x 8              448    4       64      2        9 x 2        72 KB
+//   conv3  4 x 4              128    8       64      1        9 x 4        144 KB
+//   conv4  4 x 4              128    8       128     1        9 x 4        288 KB
+//   linear 1 x 1              8      16      128     1        1 x 8        64 KB
+//
+// Precision: v = hi + lo with hi = fp16(v * 2^e), lo = fp16(v * 2^e - hi); products hi*hi + lo*hi + hi*lo accumulate
+// in fp32 (TMEM).  e is chosen per agent and layer from the running maximum (two-pass epilogue), weights are scaled per
+// layer; residual ~2^-22 per product.  For N <= 64 the filter operand is [W_hi | W_lo] side by side, so A_hi needs one
+// MMA of width 2N (M=128 MMAs cost ~47-65 cycles whatever N <= 128 is: the A read bounds them) and the two halves of
+// the accumulator are added in the epilogue.
+//
+// Roles: warp 0 = MMA issuer, warp 1 = loader (filter chunks through a 5 x 16 KB ring of bulk copies, input tiles),
+// warps 2-9 = epilogue (TMEM -> BatchNorm/ReLU/max-pool -> fp16 split -> next layer's operand buffer).
+#include "common.cuh"
+#include "feature.cuh"
+#include "tc_common.cuh"
+
+#include <cuda_fp16.h>
+#include <stdio.h>
+
+namespace gpp {
+
+constexpr int FM_A = 8;                        // agents per tile
+constexpr int FM_EPI_WARPS = 8;
+constexpr int FM_EPI_THREADS = 32 * FM_EPI_WARPS;
+constexpr int FM_THREADS = 64 + FM_EPI_THREADS;
+constexpr int FM_SLOTS = 5, FM_SLOT_BYTES = 16384;
+constexpr int FM_NL = 6;
+
+__host__ __device__ constexpr int fm_n(int L) { return L < 2 ? 32 : L < 4 ? 64 : 128; }
+__host__ __device__ constexpr int fm_wp(int L) { return L == 0 ? 16 : L == 1 ? 7 : L == 2 ? 8 : L < 5 ? 4 : 1; }
+__host__ __device__ constexpr int fm_hp(int L) { return L == 0 ? 13 : L < 3 ? 7 : L < 5 ? 4 : 1; }
+__host__ __device__ constexpr int fm_aw(int L) { return FM_A * fm_wp(L); }
+__host__ __device__ constexpr int fm_rows(int L) { return fm_hp(L) * fm_aw(L); }
+__host__ __device__ constexpr int fm_planes(int L) { return L == 0 ? 1 : L < 3 ? 4 : L < 5 ? 8 : 16; }
+__host__ __device__ constexpr int fm_lbo(int L) { return fm_rows(L) * 16; }
+__host__ __device__ constexpr int fm_tiles(int L) { return L == 0 ? 10 : L == 1 ? 3 : L == 2 ? 2 : 1; }
+__host__ __device__ constexpr int fm_hout(int L) { return L == 0 ? 10 : L == 1 ? 5 : L == 2 ? 4 : L < 5 ? 2 : 1; }
+__host__ __device__ constexpr int fm_ks(int L) { return L < 3 ? 2 : L < 5 ? 4 : 8; }           // K=16 steps per tap
+__host__ __device__ constexpr int fm_taps(int L) { return L == 5 ? 1 : 9; }
+__host__ __device__ constexpr int fm_units(int L) { return L == 0 ? 1 : fm_taps(L) * fm_ks(L); }
+__host__ __device__ constexpr int fm_unit_bytes(int L) { return L == 0 ? 12288 : L < 4 ? 64 * fm_n(L) : 8192; }
+__host__ __device__ constexpr int fm_upc(int L) { return L == 0 ? 1 : L == 1 ? 8 : L < 4 ? 4 : 2; }   // units per chunk
+__host__ __device__ constexpr int fm_chunks(int L) { return (fm_units(L) + fm_upc(L) - 1) / fm_upc(L); }
+__host__ __device__ constexpr int fm_img_bytes(int L) { return fm_units(L) * fm_unit_bytes(L); }
+constexpr int FM_TOTAL_CHUNKS = fm_chunks(0) + fm_chunks(1) + fm_chunks(2) + fm_chunks(3) + fm_chunks(4) + fm_chunks(5);
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr int FM_R1 = 0;                           // in0 (hi|lo) -> act2 -> act4
+constexpr int FM_R1_BYTES = 57344;
+constexpr int FM_R2 = FM_R1 + FM_R1_BYTES;         // act1 -> act3 -> act5
+constexpr int FM_R2_BYTES = 50176;
+constexpr int FM_XRAW = FM_R2 + FM_R2_BYTES;       // raw fp32 inputs of the tile (bulk copy target)
+constexpr int FM_XRAW_BYTES = 11648;
+constexpr int FM_STG = FM_XRAW + FM_XRAW_BYTES;    // pooling partners that live in another warp
+constexpr int FM_STG_BYTES = 8192;
+constexpr int FM_RING = FM_STG + FM_STG_BYTES;
+constexpr int FM_MISC = FM_RING + FM_SLOTS * FM_SLOT_BYTES;
+constexpr int FM_SMEM_BYTES = FM_MISC + 1024;
+static_assert(2 * fm_planes(0) * fm_lbo(0) <= FM_R1_BYTES && 2 * fm_planes(2) * fm_lbo(2) <= FM_R1_BYTES, "R1");
+static_assert(2 * fm_planes(1) * fm_lbo(1) <= FM_R2_BYTES && 2 * fm_planes(3) * fm_lbo(3) <= FM_R2_BYTES, "R2");
+static_assert(FM_SMEM_BYTES <= 232448, "shared memory budget");
+__host__ __device__ constexpr int fm_in_base(int L) { return (L == 0 || L == 2 || L == 4) ? FM_R1 : FM_R2; }
+
+struct FmMisc {
+    uint64_t w_full[FM_SLOTS], w_free[FM_SLOTS];
+    uint64_t acc0_full[2], acc0_free[2];
+    uint64_t layer_full, act_ready, xraw_full, xraw_free;
+    uint32_t tmem_slot;
+    uint32_t xflag[2];                 // tile has a non-zero lo part in its inputs
+    uint32_t amax[FM_NL][FM_A];        // running max (float bits, values >= 0) of layer L's output per agent
+    float mul0[FM_A], inv0[FM_A];      // input scale 2^e0 and its inverse
+    float mul1[FM_A], inv1[FM_A];      // act1 scale (from the weight-norm bound of conv0) and its inverse
+};
+static_assert(sizeof(FmMisc) <= 1024, "misc block");
+
+// constants block in global memory (floats): [L][0][c] = epilogue scale, [L][1][c] = shift; then misc
+constexpr int FM_CONST_MISC = FM_NL * 2 * 128;
+constexpr int FM_CONST_FLOATS = FM_CONST_MISC + 16;
+
+struct FmArgs {
+    const float* x;
+    float* feat;
+    int total_agents, num_tiles;
+    const unsigned char* img[FM_NL];
+    const float* consts;
+    int x_bulk;     // the inputs may be fetched with bulk copies (device memory, 16-byte aligned)
+    int pdl;
+    unsigned long long* timing;
+};
+
+// ---- waits -------------------------------------------------------------------------------------------------------
+constexpr long long FM_WATCHDOG_CYCLES = 2000000000LL;
+__device__ __noinline__ void fm_watchdog_trap(int id, uint32_t parity) {
+    printf("feature_mma_kernel: watchdog -- block %d warp %d stuck on barrier %d parity %u\n", (int)blockIdx.x,
+           (int)(threadIdx.x >> 5), id, parity);
+    __trap();
+}
+__device__ __forceinline__ bool fm_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fm_wait(uint64_t* bar, uint32_t parity, int id) {
+    if (fm_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!fm_try_wait(bar, parity))
+        if (clock64() - t0 > FM_WATCHDOG_CYCLES) fm_watchdog_trap(id, parity);
+}
+__device__ __forceinline__ void fm_wait_warp(uint64_t* bar, uint32_t parity, int id) {
+    if ((threadIdx.x & 31) == 0) fm_wait(bar, parity, id);
+    __syncwarp();
+}
+__device__ __forceinline__ void fm_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fm_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) fm_arrive(bar);
+}
+__device__ __forceinline__ void fm_epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ---- UMMA helpers (no-swizzle K-major descriptors, kind::f16) --------------------------------------------------------
+__device__ __forceinline__ uint64_t fm_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void fm_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void fm_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void fm_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// scale exponent for a running maximum m >= 0 (float bits): m * 2^e in [2^9, 2^10)
+__device__ __forceinline__ int fm_scale_exp(uint32_t bits) {
+    if (bits == 0) return 0;
+    int e = 9 - ((int)(bits >> 23) - 127);
+    return e < -110 ? -110 : (e > 110 ? 110 : e);
+}
+__device__ __forceinline__ float fm_pow2(int e) { return __int_as_float((e + 127) << 23); }
+
+// 8 floats -> 8 x fp16 hi (16 B) and 8 x fp16 lo
+__device__ __forceinline__ void fm_split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void fm_sts16(uint32_t addr, const uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- MMA issue of one layer (L >= 1) -------------------------------------------------------------------------------
+template <int L>
+__device__ __forceinline__ void fm_issue_layer(uint32_t sm_base, uint32_t tmem, FmMisc* ms, uint32_t& g) {
+    constexpr int N = fm_n(L), KS = fm_ks(L), UNITS = fm_units(L), UPC = fm_upc(L), UB = fm_unit_bytes(L);
+    constexpr int AW = fm_aw(L), LBO = (L == 5) ? 128 : fm_lbo(L), TILES = fm_tiles(L);
+    constexpr uint32_t A_HI = fm_in_base(L), A_LO = fm_in_base(L) + fm_planes(L) * LBO;
+    constexpr int DCOLS = (L <= 3) ? 2 * N : N;
+    for (int cc = 0; cc < fm_chunks(L); ++cc, ++g) {
+        const uint32_t slot = g % FM_SLOTS, use = g / FM_SLOTS;
+        fm_wait(&ms->w_full[slot], use & 1, 10 + slot);
+        tcgen05_fence_after();
+        const uint32_t bslot = sm_base + FM_RING + slot * FM_SLOT_BYTES;
+        const int nu = (UNITS - cc * UPC) < UPC ? (UNITS - cc * UPC) : UPC;
+        for (int uu = 0; uu < nu; ++uu) {
+            const int u = cc * UPC + uu;
+            const int tap = u / KS, k16 = u - tap * KS;
+            const int shift = (L == 5) ? 0 : ((tap / 3) * AW + (tap % 3));
+            const uint32_t boff = bslot + uu * UB;
+#pragma unroll
+            for (int t = 0; t < TILES; ++t) {
+                const uint32_t aoff = (uint32_t)((t * 128 + shift) * 16 + k16 * 2 * LBO);
+                const uint64_t da_hi = fm_desc(sm_base + A_HI + aoff, LBO, 128);
+                const uint64_t da_lo = fm_desc(sm_base + A_LO + aoff, LBO, 128);
+                const uint32_t d = tmem + t * DCOLS;
+                if (L <= 3) {
+                    const uint64_t db = fm_desc(boff, 32 * N, 128);         // planes of [W_hi | W_lo]: 2N rows of 16 B
+                    fm_mma(d, da_hi, db, umma_idesc_f16(128, 2 * N), u > 0);
+                    fm_mma(d, da_lo, db, umma_idesc_f16(128, N), 1);
+                } else {
+                    const uint64_t db_hi = fm_desc(boff, 2048, 128), db_lo = fm_desc(boff + 4096, 2048, 128);
+                    fm_mma(d, da_hi, db_hi, umma_idesc_f16(128, 128), u > 0);
+                    fm_mma(d, da_lo, db_hi, umma_idesc_f16(128, 128), 1);
+                    fm_mma(d, da_hi, db_lo, umma_idesc_f16(128, 128), 1);
+                }
+            }
+        }
+        umma_commit(&ms->w_free[slot]);
+    }
+    umma_commit(&ms->layer_full);
+}
+
+// ---- epilogue pieces -----------------------------------------------------------------------------------------------
+// 16 output channels [c0, c0+16) of this thread's row of M tile `t` of layer L: accumulator (both halves for the
+// [W_hi | W_lo] layers) * inv -> folded BatchNorm / bias -> ReLU
+template <int L>
+__device__ __forceinline__ void fm_row_vals(uint32_t tmem_lane, int t, int c0, float inv, const float* __restrict__ cst,
+                                            float (&u)[16]) {
+    constexpr int N = fm_n(L);
+    constexpr int DCOLS = (L <= 3) ? 2 * N : N;
+    float a[16];
+    fm_tmem_ld16(tmem_lane + t * DCOLS + c0, a);
+    if (L <= 3) {
+        float b[16];
+        fm_tmem_ld16(tmem_lane + t * DCOLS + N + c0, b);
+        fm_tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] += b[i];
+    } else {
+        fm_tmem_wait_ld();
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(cst + (L * 2) * 128 + c0 + i));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(cst + (L * 2 + 1) * 128 + c0 + i));
+        u[i] = fmaxf(fmaf(a[i] * inv, sc.x, sh.x), 0.f);
+        u[i + 1] = fmaxf(fmaf(a[i + 1] * inv, sc.y, sh.y), 0.f);
+        u[i + 2] = fmaxf(fmaf(a[i + 2] * inv, sc.z, sh.z), 0.f);
+        u[i + 3] = fmaxf(fmaf(a[i + 3] * inv, sc.w, sh.w), 0.f);
+    }
+}
+__device__ __forceinline__ float fm_max16(const float (&u)[16]) {
+    float m = u[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) m = fmaxf(m, u[i]);
+    return m;
+}
+// store 16 scaled channels as two (hi, lo) 16-byte pairs: planes c0/8 and c0/8+1 of the buffer at `base`
+__device__ __forceinline__ void fm_store16(uint32_t base, int lbo, int planes, int row, int c0, const float (&u)[16], float mul) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = u[i] * mul;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        uint4 hi, lo;
+        fm_split8(v + 8 * p, hi, lo);
+        const uint32_t addr = base + ((c0 >> 3) + p) * lbo + row * 16;
+        fm_sts16(addr, hi);
+        fm_sts16(addr + planes * lbo, lo);
+    }
+}
+__device__ __forceinline__ void fm_zero(uint32_t addr, int bytes, int et) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = et * 16; i < bytes; i += FM_EPI_THREADS * 16) fm_sts16(addr + i, z);
+}
+
+// dynamic-scale layers 1..4: zero the target buffer, wait for the accumulators, pass 1 = per-agent maximum (+ pooling
+// partners that live in another warp go through FM_STG), pass 2 = pool, scale, split, store
+template <int L>
+__device__ __forceinline__ void fm_epilogue_dyn(unsigned char* sm, uint32_t sm_base, uint32_t tmem_lane, FmMisc* ms,
+                                                const float* __restrict__ cst, int na, int q, int h, int lane, int et,
+                                                uint32_t& gl) {
+    constexpr int N = fm_n(L), AW = fm_aw(L), WP = fm_wp(L), HO = fm_hout(L), TILES = fm_tiles(L);
+    constexpr bool POOL = (L == 2 || L == 4);
+    constexpr int LO = L + 1;                                      // the layer that consumes the output
+    constexpr uint32_t OUT = fm_in_base(LO);
+    constexpr int OLBO = (LO == 5) ? 128 : fm_lbo(LO), OPL = fm_planes(LO), OAW = fm_aw(LO), OWP = fm_wp(LO);
+    constexpr int NB = N / 32;                                     // 16-channel blocks per thread (channel half h)
+    fm_zero(sm_base + OUT, (LO == 5) ? 8192 : 2 * OPL * OLBO, et);
+    fm_wait_warp(&ms->layer_full, gl & 1, 30 + L);
+    ++gl;
+    tcgen05_fence_after();
+    float* stg = reinterpret_cast<float*>(sm + FM_STG);
+    const int l = q * 32 + lane;
+    // ---- pass 1
+    const bool rows_here = (L == 1 || L == 2) ? true : (q < 2);     // conv3 / conv4: the valid rows are lanes 0..63
+    if (rows_here) {
+#pragma unroll 1
+        for (int t = 0; t < TILES; ++t) {
+            const int r = t * 128 + l;
+            const int y = r / AW, a = (r % AW) / WP, x = r % WP;
+            const bool valid = y < HO && x < HO && a < na;
+            const float inv = (L == 1) ? ms->inv1[a] : fm_pow2(-fm_scale_exp(ms->amax[L - 1][a]));
+            float mx = 0.f;
+#pragma unroll 1
+            for (int b = 0; b < NB; ++b) {
+                const int c0 = h * (N / 2) + 16 * b;
+                float u[16];
+                fm_row_vals<L>(tmem_lane, t, c0, inv, cst, u);
+                mx = fmaxf(mx, fm_max16(u));
+                if (POOL) {
+                    // x partner by shuffle; the y partner row lives 64 (conv2) / 32 (conv4) lanes up: it parks its
+                    // x-pooled values in FM_STG
+                    const bool upper = (L == 2) ? (q >= 2) : (q == 1);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) u[i] = fmaxf(u[i], __shfl_down_sync(0xffffffffu, u[i], 1));
+                    if (upper && valid && !(x & 1)) {
+                        float* dst = stg + (((L == 2 ? t * FM_A + a : a) * (L == 2 ? 2 : 1) + (x >> 1)) * N + c0);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+                    }
+                }
+            }
+            if (valid) atomicMax(&ms->amax[L][a], __float_as_uint(mx));
+        }
+    }
+    fm_epi_sync();
+    // ---- pass 2
+    const bool writer = POOL ? ((L == 2) ? (q < 2) : (q == 0)) : rows_here;
+    if (writer) {
+#pragma unroll 1
+        for (int t = 0; t < TILES; ++t) {
+            const int r = t * 128 + l;
+            const int y = r / AW, a = (r % AW) / WP, x = r % WP;
+            const bool valid = y < HO && x < HO && a < na && (!POOL || !(x & 1));
+            const float inv = (L == 1) ? ms->inv1[a] : fm_pow2(-fm_scale_exp(ms->amax[L - 1][a]));
+            const float mul = fm_pow2(fm_scale_exp(ms->amax[L][a]));
+            int orow;
+            if (LO == 5) orow = a;
+            else if (POOL) orow = ((y >> 1) + 1) * OAW + a * OWP + (x >> 1) + 1;
+            else orow = (y + 1) * OAW + a * OWP + x + 1;
+#pragma unroll 1
+            for (int b = 0; b < NB; ++b) {
+                const int c0 = h * (N / 2) + 16 * b;
+                float u[16];
+                fm_row_vals<L>(tmem_lane, t, c0, inv, cst, u);
+                if (POOL) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) u[i] = fmaxf(u[i], __shfl_down_sync(0xffffffffu, u[i], 1));
+                    if (valid) {
+                        const float* src = stg + (((L == 2 ? t * FM_A + a : a) * (L == 2 ? 2 : 1) + (x >> 1)) * N + c0);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 p = *reinterpret_cast<const float4*>(src + i);
+                            u[i] = fmaxf(u[i], p.x); u[i + 1] = fmaxf(u[i + 1], p.y);
+                            u[i + 2] = fmaxf(u[i + 2], p.z); u[i + 3] = fmaxf(u[i + 3], p.w);
+                        }
+                    }
+                }
+                if (valid) fm_store16(sm_base + OUT, OLBO, OPL, orow, c0, u, mul);
+            }
+        }
+    }
+    tcgen05_fence_before();
+    fence_proxy_async_smem();
+    fm_arrive_warp(&ms->act_ready);
+}
+
+// =====================================================================================================================
+__global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs A) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    FmMisc* ms = reinterpret_cast<FmMisc*>(sm + FM_MISC);
+    const uint32_t sm_base = smem_u32(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FM_SLOTS; ++s) { mbar_init(&ms->w_full[s], 1); mbar_init(&ms->w_free[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&ms->acc0_full[b], 1); mbar_init(&ms->acc0_free[b], FM_EPI_WARPS); }
+        mbar_init(&ms->layer_full, 1);
+        mbar_init(&ms->act_ready, FM_EPI_WARPS);
+        mbar_init(&ms->xraw_full, 1);
+        mbar_init(&ms->xraw_free, FM_EPI_WARPS);
+        ms->xflag[0] = 0; ms->xflag[1] = 0;
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&ms->tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = ms->tmem_slot;
+    const float* __restrict__ cst = A.consts;
+    griddep_launch_dependents();       // the next kernel of the stream may start its prologue; it still waits for this grid
+
+    if (warp == 1) {
+        // ================= loader =================
+        if (lane == 0) {
+            uint32_t g = 0;
+            int it = 0;
+            auto issue_x = [&](int tile) {
+                const int na = min(FM_A, A.total_agents - tile * FM_A);
+                if (A.x_bulk && na == FM_A) {
+                    mbar_arrive_expect_tx(&ms->xraw_full, FM_A * 363 * 4);
+                    bulk_g2s(sm + FM_XRAW, A.x + (size_t)tile * FM_A * 363, FM_A * 363 * 4, &ms->xraw_full);
+                } else {
+                    fm_arrive(&ms->xraw_full);        // the epilogue warps read this tile straight from global memory
+                }
+            };
+            for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, ++it) {
+                int c = 0;
+                for (int L = 0; L < FM_NL; ++L) {
+                    const int nch = fm_chunks(L), upc = fm_upc(L), ub = fm_unit_bytes(L), units = fm_units(L);
+                    for (int cc = 0; cc < nch; ++cc, ++c, ++g) {
+                        if (it == 0 && c == FM_SLOTS - 1) {
+                            if (A.pdl) griddep_wait();
+                            issue_x(tile);
+                        }
+                        if (c == 8) {
+                            const int next = tile + gridDim.x;
+                            if (next < A.num_tiles) {
+                                fm_wait(&ms->xraw_free, it & 1, 40);
+                                issue_x(next);
+                            }
+                        }
+                        const uint32_t slot = g % FM_SLOTS, use = g / FM_SLOTS;
+                        if (use >= 1) fm_wait(&ms->w_free[slot], (use - 1) & 1, 20 + slot);
+                        const int nu = (units - cc * upc) < upc ? (units - cc * upc) : upc;
+                        const uint32_t bytes = (uint32_t)(nu * ub);
+                        mbar_arrive_expect_tx(&ms->w_full[slot], bytes);
+                        bulk_g2s(sm + FM_RING + slot * FM_SLOT_BYTES, A.img[L] + (size_t)cc * upc * ub, bytes,
+                                 &ms->w_full[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 0) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t g = 0, gp = 0, gr = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, ++it) {
+                // ---- conv0: five pairs of image rows, accumulators double-buffered in TMEM columns [256, 512)
+                fm_wait(&ms->act_ready, gr & 1, 50);
+                ++gr;
+                tcgen05_fence_after();
+                const uint32_t has_lo = *reinterpret_cast<volatile uint32_t*>(&ms->xflag[it & 1]);
+                {
+                    const uint32_t slot = g % FM_SLOTS, use = g / FM_SLOTS;
+                    fm_wait(&ms->w_full[slot], use & 1, 10 + slot);
+                    tcgen05_fence_after();
+                    const uint32_t bslot = sm_base + FM_RING + slot * FM_SLOT_BYTES;
+                    for (int j = 0; j < 5; ++j, ++gp) {
+                        const uint32_t b = gp & 1;
+                        if (gp >= 2) {
+                            fm_wait(&ms->acc0_free[b], ((gp >> 1) - 1) & 1, 52 + b);
+                            tcgen05_fence_after();
+                        }
+#pragma unroll
+                        for (int tt = 0; tt < 2; ++tt) {
+                            const int y = 2 * j + tt;
+                            const uint32_t d = tmem + 256 + b * 128 + tt * 64;
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                                for (int pr = 0; pr < 2; ++pr) {
+                                    const uint32_t aoff = (uint32_t)(((y + 2 * pr) * 128 + kx) * 16);
+                                    const uint64_t db = fm_desc(bslot + (kx * 2 + pr) * 2048, 1024, 128);
+                                    fm_mma(d, fm_desc(sm_base + FM_R1 + aoff, 2048, 128), db, umma_idesc_f16(128, 64),
+                                           (kx | pr) != 0);
+                                    if (has_lo)
+                                        fm_mma(d, fm_desc(sm_base + FM_R1 + fm_lbo(0) + aoff, 2048, 128), db,
+                                               umma_idesc_f16(128, 32), 1);
+                                }
+                        }
+                        umma_commit(&ms->acc0_full[b]);
+                    }
+                    umma_commit(&ms->w_free[slot]);
+                    ++g;
+                }
+#define FM_ISSUE(Lx)                                   \
+    fm_wait(&ms->act_ready, gr & 1, 50 + Lx);          \
+    ++gr;                                              \
+    tcgen05_fence_after();                             \
+    fm_issue_layer<Lx>(sm_base, tmem, ms, g);
+                FM_ISSUE(1) FM_ISSUE(2) FM_ISSUE(3) FM_ISSUE(4) FM_ISSUE(5)
+#undef FM_ISSUE
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int ew = warp - 2, q = warp & 3, h = ew >> 2, et = threadIdx.x - 64;
+        const int l = q * 32 + lane;
+        const uint32_t tmem_lane = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t gpe = 0, gl = 0;
+        int it = 0;
+        if (A.pdl) griddep_wait();         // x (and the feature buffer's previous readers) belong to earlier kernels
+        for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, ++it) {
+            const int na = min(FM_A, A.total_agents - tile * FM_A);
+            const bool bulk = A.x_bulk && na == FM_A;
+            // ---- inputs: per-agent scale, fp16 split into the padded in0 planes
+            if (et < FM_NL * FM_A) (&ms->amax[0][0])[et] = 0;
+            if (et == 64) ms->xflag[(it + 1) & 1] = 0;
+            fm_zero(sm_base + FM_R2, 2 * fm_planes(1) * fm_lbo(1), et);       // act1 borders
+            fm_wait_warp(&ms->xraw_full, it & 1, 41);
+            const float* xs = bulk ? reinterpret_cast<const float*>(sm + FM_XRAW) : A.x + (size_t)tile * FM_A * 363;
+            {
+                const int a = ew;      // one warp per agent
+                float m = 0.f;
+                if (a < na)
+                    for (int i = lane; i < 363; i += 32) m = fmaxf(m, fabsf(xs[a * 363 + i]));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) {
+                    const int e0 = fm_scale_exp(__float_as_uint(m));
+                    ms->mul0[a] = fm_pow2(e0);
+                    ms->inv0[a] = fm_pow2(-e0);
+                    const float bound = m * __ldg(cst + FM_CONST_MISC) + __ldg(cst + FM_CONST_MISC + 1);
+                    const int e1 = fm_scale_exp(__float_as_uint(bound));
+                    ms->mul1[a] = fm_pow2(e1);
+                    ms->inv1[a] = fm_pow2(-e1);
+                }
+            }
+            fm_epi_sync();
+            {
+                uint32_t any_lo = 0;
+                for (int row = et; row < fm_rows(0); row += FM_EPI_THREADS) {
+                    const int y = row >> 7, a = (row >> 4) & 7, x = row & 15;
+                    uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
+                    if (y >= 1 && y <= 11 && x >= 1 && x <= 11 && a < na) {
+                        const float* p = xs + a * 363 + (y - 1) * 11 + (x - 1);
+                        const float mul = ms->mul0[a];
+                        const float v0 = p[0] * mul, v1 = p[121] * mul, v2 = p[242] * mul;
+                        const __half2 h01 = __floats2half2_rn(v0, v1), h2 = __floats2half2_rn(v2, 0.f);
+                        const float2 f01 = __half22float2(h01), f2 = __half22float2(h2);
+                        const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l2 = __floats2half2_rn(v2 - f2.x, 0.f);
+                        hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h2);
+                        lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l2);
+                        any_lo |= (lo.x | lo.y) & 0x7FFF7FFFu;
+                    }
+                    fm_sts16(sm_base + FM_R1 + row * 16, hi);
+                    fm_sts16(sm_base + FM_R1 + fm_lbo(0) + row * 16, lo);
+                }
+                if (__any_sync(0xffffffffu, any_lo != 0) && lane == 0) atomicOr(&ms->xflag[it & 1], 1u);
+            }
+            fence_proxy_async_smem();
+            fm_arrive_warp(&ms->xraw_free);
+            fm_epi_sync();                     // xflag / act1 zeroes / in0 complete in every warp
+            fm_arrive_warp(&ms->act_ready);
+
+            // ---- conv0 epilogue: y pairs are the two accumulators of a pair, x pairs neighbouring lanes
+            {
+                const int a = l >> 4, x = l & 15;
+                const float inv = ms->inv0[a], mul = ms->mul1[a];
+                const int c0 = h * 16;
+                for (int j = 0; j < 5; ++j, ++gpe) {
+                    const uint32_t b = gpe & 1;
+                    fm_wait_warp(&ms->acc0_full[b], (gpe >> 1) & 1, 60 + b);
+                    tcgen05_fence_after();
+                    const uint32_t col = 256 + b * 128 + c0;
+                    float p0[16], p1[16], q0[16], q1[16];
+                    fm_tmem_ld16(tmem_lane + col, p0);
+                    fm_tmem_ld16(tmem_lane + col + 32, p1);
+                    fm_tmem_ld16(tmem_lane + col + 64, q0);
+                    fm_tmem_ld16(tmem_lane + col + 96, q1);
+                    fm_tmem_wait_ld();
+                    tcgen05_fence_before();
+                    fm_arrive_warp(&ms->acc0_free[b]);
+                    float u[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float sc = __ldg(cst + c0 + i), sh = __ldg(cst + 128 + c0 + i);
+                        const float u0 = fmaf((p0[i] + p1[i]) * inv, sc, sh), u1 = fmaf((q0[i] + q1[i]) * inv, sc, sh);
+                        float m = fmaxf(fmaxf(u0, u1), 0.f);
+                        u[i] = fmaxf(m, __shfl_down_sync(0xffffffffu, m, 1));
+                    }
+                    if (x < 10 && !(x & 1) && a < na)
+                        fm_store16(sm_base + FM_R2, fm_lbo(1), fm_planes(1), (j + 1) * fm_aw(1) + a * fm_wp(1) + (x >> 1) + 1,
+                                   c0, u, mul);
+                }
+                fence_proxy_async_smem();
+                fm_arrive_warp(&ms->act_ready);
+            }
+            fm_epilogue_dyn<1>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
+            fm_epilogue_dyn<2>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
+            fm_epilogue_dyn<3>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
+            fm_epilogue_dyn<4>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
+            // ---- compress MLP: rows 0..7 of the tile are the agents
+            fm_wait_warp(&ms->layer_full, gl & 1, 35);
+            ++gl;
+            tcgen05_fence_after();
+            if (q == 0) {
+                const int a = lane & 7;
+                const float inv = fm_pow2(-fm_scale_exp(ms->amax[4][a]));
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {
+                    const int c0 = h * 64 + 16 * b;
+                    float u[16];
+                    fm_row_vals<5>(tmem_lane, 0, c0, inv, cst, u);
+                    if (lane < 8 && a < na) {
+                        float* dst = A.feat + (size_t)(tile * FM_A + a) * 128 + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            fm_epi_sync();      // every warp is done with this tile's shared state before the next tile resets it
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// =====================================================================================================================
+// Weight preparation: per-layer power-of-two scale from max|w|, fp16 (hi, lo) images in chunk order, epilogue constants
+// =====================================================================================================================
+__global__ void fm_absmax_kernel(const float* __restrict__ w, int n, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+
+__device__ __forceinline__ __half fm_pick(float v, int islo) {
+    const __half hi = __float2half_rn(v);
+    return islo ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+
+// one thread per fp16 element of layer L's image
+__global__ void fm_prep_image_kernel(const float* __restrict__ w, __half* __restrict__ img, int L,
+                                     const unsigned int* __restrict__ amax) {
+    const int N = fm_n(L), idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= fm_img_bytes(L) / 2) return;
+    const float mul = fm_pow2(fm_scale_exp(amax[L]));
+    const int e = idx & 7;
+    float v = 0.f;
+    int islo = 0;
+    if (L == 0) {
+        // [kx][pr][plane][n2 (64 = hi | lo)][8]
+        int r = idx >> 3;
+        const int n2 = r & 63; r >>= 6;
+        const int p = r & 1; r >>= 1;
+        const int pr = r & 1, kx = r >> 1;
+        const int ky = 2 * pr + p, n = n2 & 31;
+        islo = n2 >> 5;
+        if (ky < 3 && e < 3) v = w[(n * 3 + e) * 9 + ky * 3 + kx];
+    } else if (L <= 3) {
+        // [unit][plane][n2 (2N = hi | lo)][8]
+        const int Cin = fm_planes(L) * 8, KS = fm_ks(L);
+        int r = idx >> 3;
+        const int n2 = r % (2 * N); r /= 2 * N;
+        const int p = r & 1, u = r >> 1;
+        const int tap = u / KS, k16 = u - tap * KS, ci = k16 * 16 + p * 8 + e, n = n2 % N;
+        islo = n2 / N;
+        v = w[((size_t)n * Cin + ci) * 9 + tap];
+    } else {
+        // [unit][hi | lo][plane][n (128)][8]
+        const int Cin = fm_planes(L) * 8, KS = fm_ks(L);
+        int r = idx >> 3;
+        const int n = r & 127; r >>= 7;
+        const int p = r & 1; r >>= 1;
+        islo = r & 1;
+        const int u = r >> 1;
+        const int tap = u / KS, k16 = u - tap * KS, ci = k16 * 16 + p * 8 + e;
+        v = (L == 5) ? w[(size_t)n * 128 + ci] : w[((size_t)n * Cin + ci) * 9 + tap];
+    }
+    img[idx] = fm_pick(v * mul, islo);
+}
+
+// epilogue constants: [L][0][c] = BatchNorm scale / 2^ew_L, [L][1][c] = shift; misc[0] = max_c |sc_c| * sum|w_c| of conv0,
+// misc[1] = max_c |sh_c| of conv0 (bound of conv0's output for inputs of magnitude <= 1)
+__global__ void fm_prep_consts_kernel(const float* const* sc, const float* const* sh, const float* b5, const float* w0,
+                                      const unsigned int* __restrict__ amax, float* __restrict__ cst) {
+    const int c = threadIdx.x;      // 128 threads
+    for (int L = 0; L < FM_NL; ++L) {
+        const float inv = fm_pow2(-fm_scale_exp(amax[L]));
+        float s = 0.f, t = 0.f;
+        if (c < fm_n(L)) {
+            s = (L < 5 ? sc[L][c] : 1.f) * inv;
+            t = L < 5 ? sh[L][c] : b5[c];
+        }
+        cst[(L * 2) * 128 + c] = s;
+        cst[(L * 2 + 1) * 128 + c] = t;
+    }
+    __shared__ float red[2][128];
+    float b0 = 0.f, b1 = 0.f;
+    if (c < 32) {
+        float sw = 0.f;
+        for (int i = 0; i < 27; ++i) sw += fabsf(w0[c * 27 + i]);
+        b0 = fabsf(sc[0][c]) * sw;
+        b1 = fabsf(sh[0][c]);
+    }
+    red[0][c] = b0; red[1][c] = b1;
+    __syncthreads();
+    if (c == 0) {
+        float m0 = 0.f, m1 = 0.f;
+        for (int i = 0; i < 32; ++i) { m0 = fmaxf(m0, red[0][i]); m1 = fmaxf(m1, red[1][i]); }
+        cst[FM_CONST_MISC] = m0;
+        cst[FM_CONST_MISC + 1] = m1;
+    }
+}
+
+size_t feature_mma_arena_floats() {
+    size_t bytes = 0;
+    for (int L = 0; L < FM_NL; ++L) bytes += fm_img_bytes(L);
+    return bytes / 4 + FM_CONST_FLOATS + 64 /* amax + pointer table */;
+}
+
+// arena layout (floats): images L0..L5 | consts | amax[8] | pointer table (sc[5], sh[5] as 64-bit)
+int launch_prep_feature_mma(const float* const* conv_w, const float* compress_w, const float* const* sc,
+                            const float* const* sh, const float* b5, float* arena, cudaStream_t st) {
+    size_t off = 0;
+    unsigned char* base = reinterpret_cast<unsigned char*>(arena);
+    size_t img_off[FM_NL];
+    for (int L = 0; L < FM_NL; ++L) { img_off[L] = off; off += fm_img_bytes(L); }
+    float* cst = reinterpret_cast<float*>(base + off);
+    unsigned int* amax = reinterpret_cast<unsigned int*>(cst + FM_CONST_FLOATS);
+    const float** ptrs = reinterpret_cast<const float**>(amax + 8);
+    GPP_CUDA_OK(cudaMemsetAsync(amax, 0, 32, st));
+    static const int cin[6] = {3, 32, 32, 64, 64, 128};
+    for (int L = 0; L < FM_NL; ++L) {
+        const float* w = L < 5 ? conv_w[L] : compress_w;
+        const int n = L < 5 ? fm_n(L) * cin[L] * 9 : 128 * 128;
+        fm_absmax_kernel<<<32, 256, 0, st>>>(w, n, amax + L);
+        GPP_LAUNCH_CHECK();
+    }
+    for (int L = 0; L < FM_NL; ++L) {
+        const int n = fm_img_bytes(L) / 2;
+        fm_prep_image_kernel<<<(n + 255) / 256, 256, 0, st>>>(L < 5 ? conv_w[L] : compress_w,
+                                                              reinterpret_cast<__half*>(base + img_off[L]), L, amax);
+        GPP_LAUNCH_CHECK();
+    }
+    const float* host_ptrs[10];
+    for (int l = 0; l < 5; ++l) { host_ptrs[l] = sc[l]; host_ptrs[5 + l] = sh[l]; }
+    GPP_CUDA_OK(cudaMemcpyAsync(ptrs, host_ptrs, sizeof(host_ptrs), cudaMemcpyHostToDevice, st));
+    GPP_CUDA_OK(cudaStreamSynchronize(st));          // host_ptrs is a stack array
+    fm_prep_consts_kernel<<<1, 128, 0, st>>>(ptrs, ptrs + 5, b5, conv_w[0], amax, cst);
+    GPP_LAUNCH_CHECK();
+    return GPP_OK;
+}
+
+static unsigned long long* g_fm_timing = nullptr;
+int debug_feature_mma_timing(unsigned long long* out32) {
+    if (!g_fm_timing) return GPP_ERR_INVALID;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out32, g_fm_timing, 256, cudaMemcpyDeviceToHost);
+    cudaMemset(g_fm_timing, 0, 256);
+    return GPP_OK;
+}
+
+int launch_feature_mma_kernel(const FeArgs& fa, const float* arena, int x_bulk, cudaStream_t st) {
+    FmArgs a;
+    a.x = fa.x; a.feat = fa.feat; a.total_agents = fa.total_agents;
+    a.num_tiles = (fa.total_agents + FM_A - 1) / FM_A;
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(arena);
+    size_t off = 0;
+    for (int L = 0; L < FM_NL; ++L) { a.img[L] = base + off; off += fm_img_bytes(L); }
+    a.consts = reinterpret_cast<const float*>(base + off);
+    a.x_bulk = (x_bulk && (reinterpret_cast<uintptr_t>(fa.x) & 15) == 0) ? 1 : 0;
+    a.pdl = fa.pdl;
+    a.timing = nullptr;
+    if (debug_option(DBG_TC_TIMING)) {
+        if (!g_fm_timing) { cudaMalloc(&g_fm_timing, 256); cudaMemset(g_fm_timing, 0, 256); }
+        a.timing = g_fm_timing;
+    }
+    static SmemConfig smem_cfg;
+    GPP_CUDA_OK(ensure_dynamic_smem(feature_mma_kernel, smem_cfg, FM_SMEM_BYTES));
+    const int grid = a.num_tiles < sm_count() ? a.num_tiles : sm_count();
+    GPP_CUDA_OK(launch_maybe_pdl(feature_mma_kernel, grid, FM_THREADS, FM_SMEM_BYTES, st, fa.pdl, a));
+    GPP_LAUNCH_CHECK();
+    return GPP_OK;
+}
+
+}  // namespace gpp

@@ -98,6 +98,12 @@ size_t feature_tc_image_floats(int L);
 int launch_prep_feature_tc(const float* w, float* img, int L, cudaStream_t st);
 int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStream_t st);
 int debug_feature_tc_timing(unsigned long long* out20);
+// im2col-free fp16-split tensor-core feature extractor (feature_mma.cu)
+size_t feature_mma_arena_floats();
+int launch_prep_feature_mma(const float* const* conv_w, const float* compress_w, const float* const* sc,
+                            const float* const* sh, const float* b5, float* arena, cudaStream_t st);
+int launch_feature_mma_kernel(const FeArgs& fa, const float* arena, int x_bulk, cudaStream_t st);
+int debug_feature_mma_timing(unsigned long long* out32);
 int debug_feature_timing(unsigned long long* out7);
 
 // scale = gamma / sqrt(var + eps);  shift = (conv_bias - mean) * scale + beta
@@ -133,7 +139,8 @@ struct gpp_planner {
     bool pdl_ok;         // the kernels before the next forward in its stream only wrote what it reads after its
                          // griddepcontrol.wait (false right after the weights were re-staged)
     int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 3xTF32 kernel, 3 tcgen05 CTA-pair fp16-split kernel
-    int fe_mode;         // feature extractor: 0 auto, 1 CUDA-core kernel, 2 tcgen05 kernel
+    int fe_mode;         // feature extractor: 0 auto, 1 CUDA-core kernel, 2 tcgen05 3xTF32 kernel, 3 tcgen05 fp16-split kernel
+    size_t off_fmma;     // images + constants of the fp16-split kernel
     size_t off_fimg[6];  // tcgen05 filter chunk images of conv0..4 and the compress MLP
     bool weights_set;
     float* raw;          // device staging for host-provided parameters
@@ -210,6 +217,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     p->off_gfimg = take(gf_tc_image_floats(K));      // pre-split, pre-swizzled tcgen05 B-operand chunks
     p->off_gfpair = take(K <= 3 ? gf_pair_image_bytes(K) / 4 + 16 : 16);
     for (int l = 0; l < 6; ++l) p->off_fimg[l] = take(feature_tc_image_floats(l));
+    p->off_fmma = take(feature_mma_arena_floats());
     p->arena_floats = off;
     if (cudaMalloc(&p->arena, sizeof(float) * off) != cudaSuccess) {
         set_error("planner_create: cudaMalloc(%zu) failed", sizeof(float) * off);
@@ -276,7 +284,7 @@ extern "C" int gpp_debug_set_option(const char* name, int value) {
 }
 
 extern "C" int gpp_planner_set_feature_mode(gpp_planner* p, int mode) {
-    GPP_REQUIRE(p && mode >= 0 && mode <= 2, GPP_ERR_INVALID, "planner_set_feature_mode: mode must be 0, 1 or 2");
+    GPP_REQUIRE(p && mode >= 0 && mode <= 3, GPP_ERR_INVALID, "planner_set_feature_mode: mode must be 0, 1, 2 or 3");
     p->fe_mode = mode;
     return GPP_OK;
 }
@@ -404,6 +412,14 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     }
     int rc = launch_transpose_taps(d.compress_w, A + p->off_w[5], 128, 128, st);
     if (rc) return rc;
+    GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_b5, d.compress_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
+    {
+        const float* scp[5];
+        const float* shp[5];
+        for (int l = 0; l < 5; ++l) { scp[l] = A + p->off_sc[l]; shp[l] = A + p->off_sh[l]; }
+        rc = launch_prep_feature_mma(d.conv_w, d.compress_w, scp, shp, A + p->off_b5, A + p->off_fmma, st);
+        if (rc) return rc;
+    }
     rc = launch_transpose_taps(d.gf_w, A + p->off_gfw, 128, K * 128, st);
     if (rc) return rc;
     rc = launch_split_taps(A + p->off_gfw, A + p->off_gfws, K * 128, st);
@@ -494,7 +510,9 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     int rc;
     // auto = the register-tiled CUDA-core kernel at every size: it is 5-10 % faster than the tcgen05 kernel even at
     // 40,960 agents per launch (profiles/r01_planner_microbench.txt); the tcgen05 kernel runs on request only
-    if (p->fe_mode == 2) {
+    if (p->fe_mode == 3) {
+        rc = launch_feature_mma_kernel(fa, A + p->off_fmma, allow_bulk, st);
+    } else if (p->fe_mode == 2) {
         const float* imgs[6];
         for (int l = 0; l < 6; ++l) imgs[l] = A + p->off_fimg[l];
         rc = launch_feature_tc_kernel(fa, imgs, st);

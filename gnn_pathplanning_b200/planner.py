@@ -354,7 +354,7 @@ class DecentralPlannerNet(nn.Module):
 
     def set_feature_mode(self, mode: str) -> None:
         """Feature extractor kernel: 'auto' (default), 'cuda' (fp32 CUDA cores) or 'tc' (tcgen05 3xTF32)."""
-        self.__dict__["_fe_mode"] = {"auto": 0, "cuda": 1, "tc": 2}[mode]
+        self.__dict__["_fe_mode"] = {"auto": 0, "cuda": 1, "tc": 2, "mma": 3}[mode]
 
     def _forward_fused(self, x, S):
         B, N = x.shape[0], x.shape[1]
