@@ -46,7 +46,7 @@ EXPORTED = (
 # test / profiling hooks declared in include/gnnpp_b200_debug.h (not part of the drop-in boundary)
 DEBUG_EXPORTED = (
     "gpp_debug_set_option", "gpp_debug_umma_selftest", "gpp_debug_tc_timing", "gpp_debug_pair_timing", "gpp_debug_gf_timing",
-    "gpp_debug_feature_tc_timing", "gpp_debug_feature_timing", "gpp_debug_train_kernel",
+    "gpp_debug_feature_tc_timing", "gpp_debug_feature_mma_timing", "gpp_debug_feature_timing", "gpp_debug_train_kernel",
 )
 
 
@@ -194,6 +194,8 @@ def load():
         lib.gpp_debug_feature_timing.restype = i
         lib.gpp_debug_feature_timing.argtypes = [C.POINTER(C.c_ulonglong)]
         lib.gpp_debug_feature_tc_timing.restype = i
+        lib.gpp_debug_feature_mma_timing.restype = i
+        lib.gpp_debug_feature_mma_timing.argtypes = [C.POINTER(C.c_ulonglong)]
         lib.gpp_debug_feature_tc_timing.argtypes = [C.POINTER(C.c_ulonglong)]
         lib.gpp_planner_set_profiling.restype = i
         lib.gpp_planner_set_profiling.argtypes = [vp, i]

@@ -12,7 +12,8 @@
 // y-major order the rows a layer needs (y < Hout) are a prefix, so M covers needed image rows only.
 //
 //   layer  in grid (Hp x Wp)  rows   planes  out ch  M tiles  taps x k16   B bytes
-//   conv0  13 x 16 (11+pad)   1664   1       32      10       3 x 2 (*)    12 KB   (*) two ky taps per K=16: LBO = one row
+//   conv0  13 x 16 (11+pad)   1664   1       32      10       3 x 2 (*)    6 KB    (*) two ky taps per K=16: LBO = one row;
+//                                                                               W_hi and W_lo share the 8-channel K slot
 //   conv1  7 x 7              392    4       32      3        9 x 2        36 KB
 //   conv2  7 x 8              448    4       64      2        9 x 2        72 KB
 //   conv3  4 x 4              128    8       64      1        9 x 4        144 KB
@@ -55,11 +56,10 @@ __host__ __device__ constexpr int fm_hout(int L) { return L == 0 ? 10 : L == 1 ?
 __host__ __device__ constexpr int fm_ks(int L) { return L < 3 ? 2 : L < 5 ? 4 : 8; }           // K=16 steps per tap
 __host__ __device__ constexpr int fm_taps(int L) { return L == 5 ? 1 : 9; }
 __host__ __device__ constexpr int fm_units(int L) { return L == 0 ? 1 : fm_taps(L) * fm_ks(L); }
-__host__ __device__ constexpr int fm_unit_bytes(int L) { return L == 0 ? 12288 : L < 4 ? 64 * fm_n(L) : 8192; }
+__host__ __device__ constexpr int fm_unit_bytes(int L) { return L == 0 ? 6144 : L < 4 ? 64 * fm_n(L) : 8192; }
 __host__ __device__ constexpr int fm_upc(int L) { return L == 0 ? 1 : L == 1 ? 8 : L < 4 ? 4 : 2; }   // units per chunk
 __host__ __device__ constexpr int fm_chunks(int L) { return (fm_units(L) + fm_upc(L) - 1) / fm_upc(L); }
 __host__ __device__ constexpr int fm_img_bytes(int L) { return fm_units(L) * fm_unit_bytes(L); }
-constexpr int FM_TOTAL_CHUNKS = fm_chunks(0) + fm_chunks(1) + fm_chunks(2) + fm_chunks(3) + fm_chunks(4) + fm_chunks(5);
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int FM_R1 = 0;                           // in0 (hi|lo) -> act2 -> act4
@@ -71,7 +71,9 @@ constexpr int FM_XRAW_BYTES = 11648;
 constexpr int FM_STG = FM_XRAW + FM_XRAW_BYTES;    // pooling partners that live in another warp
 constexpr int FM_STG_BYTES = 8192;
 constexpr int FM_RING = FM_STG + FM_STG_BYTES;
-constexpr int FM_MISC = FM_RING + FM_SLOTS * FM_SLOT_BYTES;
+constexpr int FM_CST = FM_RING + FM_SLOTS * FM_SLOT_BYTES;      // epilogue constants [L][scale | shift][128] floats
+constexpr int FM_CST_BYTES = 6 * 2 * 128 * 4;
+constexpr int FM_MISC = FM_CST + FM_CST_BYTES;
 constexpr int FM_SMEM_BYTES = FM_MISC + 1024;
 static_assert(2 * fm_planes(0) * fm_lbo(0) <= FM_R1_BYTES && 2 * fm_planes(2) * fm_lbo(2) <= FM_R1_BYTES, "R1");
 static_assert(2 * fm_planes(1) * fm_lbo(1) <= FM_R2_BYTES && 2 * fm_planes(3) * fm_lbo(3) <= FM_R2_BYTES, "R2");
@@ -147,6 +149,12 @@ __device__ __forceinline__ uint64_t fm_desc(uint32_t addr, uint32_t lbo, uint32_
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
 }
+// Issued from an `if (lane == 0)` region the compiler wraps every tcgen05.mma in a lane loop (ELECT / R2UR.BROADCAST /
+// BRA.U.ANY), ~50 cycles per instruction -- about the 47-65 cycles the tensor pipe needs for an M=128 MMA, so the pipe
+// stays busy.  A PREDICATED second MMA doubles that (the loop runs whether or not the predicate holds), which is why
+// conv0 has two separate code paths; electing a lane per instruction with all lanes running the loops (CUTLASS' way)
+// measured slower here: ~70 cycles per MMA (profiles/r02_fm_phase_timing.txt).
+__device__ __forceinline__ void fm_commit(uint64_t* bar) { umma_commit(bar); }
 __device__ __forceinline__ void fm_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -196,60 +204,89 @@ __device__ __forceinline__ void fm_sts16(uint32_t addr, const uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// debug phase timers (A.timing != null): slots 0-5 MMA wait-for-input per layer, 6-11 MMA wait-for-filters, 12-17 MMA issue,
+// 18 tiles, 19 convert, 20-25 epilogue wait-for-accumulator per layer, 26-31 epilogue work per layer (warp 2 of block 0)
+#define FM_T0() const long long _t0 = timing ? clock64() : 0
+#define FM_ACC(slot) do { if (timing) tacc[slot] += (unsigned long long)(clock64() - _t0); } while (0)
+
 // ---- MMA issue of one layer (L >= 1) -------------------------------------------------------------------------------
-template <int L>
-__device__ __forceinline__ void fm_issue_layer(uint32_t sm_base, uint32_t tmem, FmMisc* ms, uint32_t& g) {
-    constexpr int N = fm_n(L), KS = fm_ks(L), UNITS = fm_units(L), UPC = fm_upc(L), UB = fm_unit_bytes(L);
-    constexpr int AW = fm_aw(L), LBO = (L == 5) ? 128 : fm_lbo(L), TILES = fm_tiles(L);
-    constexpr uint32_t A_HI = fm_in_base(L), A_LO = fm_in_base(L) + fm_planes(L) * LBO;
-    constexpr int DCOLS = (L <= 3) ? 2 * N : N;
-    for (int cc = 0; cc < fm_chunks(L); ++cc, ++g) {
-        const uint32_t slot = g % FM_SLOTS, use = g / FM_SLOTS;
-        fm_wait(&ms->w_full[slot], use & 1, 10 + slot);
+// Everything but the ring slot is a compile-time constant: the loops are fully unrolled and a descriptor is one 32-bit
+// add on its low word (address field; smem addresses < 256 KB never carry into the LBO field at bit 16).  A looped
+// version that rebuilt the descriptors per instruction spent ~75-85 cycles per MMA in address arithmetic on the single
+// issuing thread (profiles/r02_fm_phase_v1.txt) -- longer than the 47-65 cycles the tensor pipe needs for it.
+constexpr uint32_t FM_DESC_HI = (128u >> 4) | (1u << 14);      // SBO = 128 B, descriptor version 1
+__device__ __forceinline__ uint64_t fm_desc_w(uint32_t lo) { return ((uint64_t)FM_DESC_HI << 32) | lo; }
+__host__ __device__ constexpr uint32_t fm_lbo_field(uint32_t lbo) { return ((lbo >> 4) & 0x3FFF) << 16; }
+
+struct FmIssue {
+    uint32_t sm16;        // shared-memory base >> 4
+    uint32_t tmem;
+    uint32_t slot, phase; // ring position of the next chunk
+};
+
+template <int L, int CC>
+__device__ __forceinline__ void fm_issue_chunks(FmIssue& is, FmMisc* ms, bool timing, unsigned long long* tacc) {
+    if constexpr (CC < fm_chunks(L)) {
+        constexpr int N = fm_n(L), KS = fm_ks(L), UNITS = fm_units(L), UPC = fm_upc(L), UB = fm_unit_bytes(L);
+        constexpr int AW = fm_aw(L), LBO = (L == 5) ? 128 : fm_lbo(L), TILES = fm_tiles(L);
+        constexpr uint32_t A_HI = fm_in_base(L), A_LO = fm_in_base(L) + fm_planes(L) * LBO;
+        constexpr int DCOLS = (L <= 3) ? 2 * N : N;
+        constexpr int NU = (UNITS - CC * UPC) < UPC ? (UNITS - CC * UPC) : UPC;
+        {
+            FM_T0();
+            fm_wait(&ms->w_full[is.slot], is.phase, 10 + is.slot);
+            FM_ACC(6 + L);
+        }
         tcgen05_fence_after();
-        const uint32_t bslot = sm_base + FM_RING + slot * FM_SLOT_BYTES;
-        const int nu = (UNITS - cc * UPC) < UPC ? (UNITS - cc * UPC) : UPC;
-        for (int uu = 0; uu < nu; ++uu) {
-            const int u = cc * UPC + uu;
+        FM_T0();
+        const uint32_t a_hi = is.sm16 + (A_HI >> 4) + fm_lbo_field(LBO), a_lo = is.sm16 + (A_LO >> 4) + fm_lbo_field(LBO);
+        const uint32_t bs = is.sm16 + ((FM_RING + is.slot * FM_SLOT_BYTES) >> 4) + fm_lbo_field(L <= 3 ? 32 * N : 2048);
+#pragma unroll
+        for (int uu = 0; uu < NU; ++uu) {
+            const int u = CC * UPC + uu;
             const int tap = u / KS, k16 = u - tap * KS;
             const int shift = (L == 5) ? 0 : ((tap / 3) * AW + (tap % 3));
-            const uint32_t boff = bslot + uu * UB;
 #pragma unroll
             for (int t = 0; t < TILES; ++t) {
-                const uint32_t aoff = (uint32_t)((t * 128 + shift) * 16 + k16 * 2 * LBO);
-                const uint64_t da_hi = fm_desc(sm_base + A_HI + aoff, LBO, 128);
-                const uint64_t da_lo = fm_desc(sm_base + A_LO + aoff, LBO, 128);
-                const uint32_t d = tmem + t * DCOLS;
+                const uint32_t aoff = (uint32_t)(((t * 128 + shift) * 16 + k16 * 2 * LBO) >> 4);
+                const uint32_t d = is.tmem + t * DCOLS;
                 if (L <= 3) {
-                    const uint64_t db = fm_desc(boff, 32 * N, 128);         // planes of [W_hi | W_lo]: 2N rows of 16 B
-                    fm_mma(d, da_hi, db, umma_idesc_f16(128, 2 * N), u > 0);
-                    fm_mma(d, da_lo, db, umma_idesc_f16(128, N), 1);
+                    const uint64_t db = fm_desc_w(bs + ((uu * UB) >> 4));     // planes of [W_hi | W_lo]: 2N rows of 16 B
+                    fm_mma(d, fm_desc_w(a_hi + aoff), db, umma_idesc_f16(128, 2 * N), u > 0);
+                    fm_mma(d, fm_desc_w(a_lo + aoff), db, umma_idesc_f16(128, N), 1);
                 } else {
-                    const uint64_t db_hi = fm_desc(boff, 2048, 128), db_lo = fm_desc(boff + 4096, 2048, 128);
-                    fm_mma(d, da_hi, db_hi, umma_idesc_f16(128, 128), u > 0);
-                    fm_mma(d, da_lo, db_hi, umma_idesc_f16(128, 128), 1);
-                    fm_mma(d, da_hi, db_lo, umma_idesc_f16(128, 128), 1);
+                    const uint64_t db_hi = fm_desc_w(bs + ((uu * UB) >> 4)), db_lo = fm_desc_w(bs + ((uu * UB + 4096) >> 4));
+                    fm_mma(d, fm_desc_w(a_hi + aoff), db_hi, umma_idesc_f16(128, 128), u > 0);
+                    fm_mma(d, fm_desc_w(a_lo + aoff), db_hi, umma_idesc_f16(128, 128), 1);
+                    fm_mma(d, fm_desc_w(a_hi + aoff), db_lo, umma_idesc_f16(128, 128), 1);
                 }
             }
         }
-        umma_commit(&ms->w_free[slot]);
+        fm_commit(&ms->w_free[is.slot]);
+        if (++is.slot == FM_SLOTS) { is.slot = 0; is.phase ^= 1; }
+        FM_ACC(12 + L);
+        fm_issue_chunks<L, CC + 1>(is, ms, timing, tacc);
     }
-    umma_commit(&ms->layer_full);
+}
+template <int L>
+__device__ __forceinline__ void fm_issue_layer(FmIssue& is, FmMisc* ms, bool timing, unsigned long long* tacc) {
+    fm_issue_chunks<L, 0>(is, ms, timing, tacc);
+    fm_commit(&ms->layer_full);
 }
 
 // ---- epilogue pieces -----------------------------------------------------------------------------------------------
-// 16 output channels [c0, c0+16) of this thread's row of M tile `t` of layer L: accumulator (both halves for the
-// [W_hi | W_lo] layers) * inv -> folded BatchNorm / bias -> ReLU
+__device__ __forceinline__ float4 fm_lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// 16 output channels of this thread's accumulator row: (acc (+ the [.. | W_lo] half)) * (scale * inv) + shift, ReLU.
+// taddr = TMEM address of the first column, cs = shared-memory constants of the first channel ([0..] scale, [128..] shift)
 template <int L>
-__device__ __forceinline__ void fm_row_vals(uint32_t tmem_lane, int t, int c0, float inv, const float* __restrict__ cst,
-                                            float (&u)[16]) {
+__device__ __forceinline__ void fm_block_vals(uint32_t taddr, const float* cs, float inv, float (&u)[16]) {
     constexpr int N = fm_n(L);
-    constexpr int DCOLS = (L <= 3) ? 2 * N : N;
     float a[16];
-    fm_tmem_ld16(tmem_lane + t * DCOLS + c0, a);
+    fm_tmem_ld16(taddr, a);
     if (L <= 3) {
         float b[16];
-        fm_tmem_ld16(tmem_lane + t * DCOLS + N + c0, b);
+        fm_tmem_ld16(taddr + N, b);
         fm_tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] += b[i];
@@ -258,130 +295,147 @@ __device__ __forceinline__ void fm_row_vals(uint32_t tmem_lane, int t, int c0, f
     }
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(cst + (L * 2) * 128 + c0 + i));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(cst + (L * 2 + 1) * 128 + c0 + i));
-        u[i] = fmaxf(fmaf(a[i] * inv, sc.x, sh.x), 0.f);
-        u[i + 1] = fmaxf(fmaf(a[i + 1] * inv, sc.y, sh.y), 0.f);
-        u[i + 2] = fmaxf(fmaf(a[i + 2] * inv, sc.z, sh.z), 0.f);
-        u[i + 3] = fmaxf(fmaf(a[i + 3] * inv, sc.w, sh.w), 0.f);
+        const float4 sc = fm_lds4(cs + i), sh = fm_lds4(cs + 128 + i);
+        u[i] = fmaxf(fmaf(a[i], sc.x * inv, sh.x), 0.f);
+        u[i + 1] = fmaxf(fmaf(a[i + 1], sc.y * inv, sh.y), 0.f);
+        u[i + 2] = fmaxf(fmaf(a[i + 2], sc.z * inv, sh.z), 0.f);
+        u[i + 3] = fmaxf(fmaf(a[i + 3], sc.w * inv, sh.w), 0.f);
     }
 }
 __device__ __forceinline__ float fm_max16(const float (&u)[16]) {
-    float m = u[0];
+    float m0 = fmaxf(u[0], u[1]), m1 = fmaxf(u[2], u[3]), m2 = fmaxf(u[4], u[5]), m3 = fmaxf(u[6], u[7]);
 #pragma unroll
-    for (int i = 1; i < 16; ++i) m = fmaxf(m, u[i]);
-    return m;
-}
-// store 16 scaled channels as two (hi, lo) 16-byte pairs: planes c0/8 and c0/8+1 of the buffer at `base`
-__device__ __forceinline__ void fm_store16(uint32_t base, int lbo, int planes, int row, int c0, const float (&u)[16], float mul) {
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = u[i] * mul;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        uint4 hi, lo;
-        fm_split8(v + 8 * p, hi, lo);
-        const uint32_t addr = base + ((c0 >> 3) + p) * lbo + row * 16;
-        fm_sts16(addr, hi);
-        fm_sts16(addr + planes * lbo, lo);
+    for (int i = 8; i < 16; i += 4) {
+        m0 = fmaxf(m0, u[i]); m1 = fmaxf(m1, u[i + 1]); m2 = fmaxf(m2, u[i + 2]); m3 = fmaxf(m3, u[i + 3]);
     }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// 2-wide max-pool along x between the lanes of a pair (even lane = even x): afterwards the even lane holds the pooled
+// channels 0-7 of the block and the odd lane channels 8-15 -- half the shuffles of a full exchange, and both lanes store
+__device__ __forceinline__ void fm_xpool(const float (&u)[16], int odd, float (&p)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = odd ? u[i] : u[i + 8];
+        const float mine = odd ? u[i + 8] : u[i];
+        p[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1));
+    }
+}
+// store 8 scaled channels as one (hi, lo) pair of 16-byte vectors in plane `plane` of the buffer at `base`
+__device__ __forceinline__ void fm_store8(uint32_t base, int lbo, int planes, int row, int plane, const float (&p)[8], float mul) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = p[i] * mul;
+    uint4 hi, lo;
+    fm_split8(v, hi, lo);
+    const uint32_t addr = base + plane * lbo + row * 16;
+    fm_sts16(addr, hi);
+    fm_sts16(addr + planes * lbo, lo);
 }
 __device__ __forceinline__ void fm_zero(uint32_t addr, int bytes, int et) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int i = et * 16; i < bytes; i += FM_EPI_THREADS * 16) fm_sts16(addr + i, z);
 }
 
-// dynamic-scale layers 1..4: zero the target buffer, wait for the accumulators, pass 1 = per-agent maximum (+ pooling
-// partners that live in another warp go through FM_STG), pass 2 = pool, scale, split, store
+// dynamic-scale layers 1..4: zero the target buffer, wait for the accumulators, pass 1 = values (kept in registers) +
+// per-agent maximum (+ pooling partners that live in another warp go through FM_STG), pass 2 = scale, split, store
 template <int L>
-__device__ __forceinline__ void fm_epilogue_dyn(unsigned char* sm, uint32_t sm_base, uint32_t tmem_lane, FmMisc* ms,
-                                                const float* __restrict__ cst, int na, int q, int h, int lane, int et,
-                                                uint32_t& gl) {
+__device__ __forceinline__ void fm_epilogue_dyn(unsigned char* sm, uint32_t sm_base, uint32_t tmem_lane, FmMisc* ms, int na,
+                                                int q, int h, int lane, int et, uint32_t& gl, bool timing,
+                                                unsigned long long* tacc) {
     constexpr int N = fm_n(L), AW = fm_aw(L), WP = fm_wp(L), HO = fm_hout(L), TILES = fm_tiles(L);
+    constexpr int DCOLS = (L <= 3) ? 2 * N : N;
     constexpr bool POOL = (L == 2 || L == 4);
     constexpr int LO = L + 1;                                      // the layer that consumes the output
     constexpr uint32_t OUT = fm_in_base(LO);
     constexpr int OLBO = (LO == 5) ? 128 : fm_lbo(LO), OPL = fm_planes(LO), OAW = fm_aw(LO), OWP = fm_wp(LO);
     constexpr int NB = N / 32;                                     // 16-channel blocks per thread (channel half h)
+    constexpr int CV = POOL ? 8 : 16;
     fm_zero(sm_base + OUT, (LO == 5) ? 8192 : 2 * OPL * OLBO, et);
-    fm_wait_warp(&ms->layer_full, gl & 1, 30 + L);
+    {
+        FM_T0();
+        fm_wait_warp(&ms->layer_full, gl & 1, 30 + L);
+        FM_ACC(20 + L);
+    }
     ++gl;
     tcgen05_fence_after();
+    FM_T0();
     float* stg = reinterpret_cast<float*>(sm + FM_STG);
-    const int l = q * 32 + lane;
-    // ---- pass 1
+    const float* cs = reinterpret_cast<const float*>(sm + FM_CST) + L * 256 + h * (N / 2);
+    const int l = q * 32 + lane, odd = lane & 1;
     const bool rows_here = (L == 1 || L == 2) ? true : (q < 2);     // conv3 / conv4: the valid rows are lanes 0..63
+    const bool upper = (L == 2) ? (q >= 2) : (q == 1);              // pooled layers: rows whose y is odd
+    float cv[TILES][NB][CV];
     if (rows_here) {
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < TILES; ++t) {
             const int r = t * 128 + l;
             const int y = r / AW, a = (r % AW) / WP, x = r % WP;
             const bool valid = y < HO && x < HO && a < na;
             const float inv = (L == 1) ? ms->inv1[a] : fm_pow2(-fm_scale_exp(ms->amax[L - 1][a]));
             float mx = 0.f;
-#pragma unroll 1
+#pragma unroll
             for (int b = 0; b < NB; ++b) {
-                const int c0 = h * (N / 2) + 16 * b;
                 float u[16];
-                fm_row_vals<L>(tmem_lane, t, c0, inv, cst, u);
+                fm_block_vals<L>(tmem_lane + t * DCOLS + h * (N / 2) + 16 * b, cs + 16 * b, inv, u);
                 mx = fmaxf(mx, fm_max16(u));
-                if (POOL) {
-                    // x partner by shuffle; the y partner row lives 64 (conv2) / 32 (conv4) lanes up: it parks its
-                    // x-pooled values in FM_STG
-                    const bool upper = (L == 2) ? (q >= 2) : (q == 1);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) u[i] = fmaxf(u[i], __shfl_down_sync(0xffffffffu, u[i], 1));
-                    if (upper && valid && !(x & 1)) {
-                        float* dst = stg + (((L == 2 ? t * FM_A + a : a) * (L == 2 ? 2 : 1) + (x >> 1)) * N + c0);
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(dst + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+                if constexpr (POOL) {
+                    fm_xpool(u, odd, cv[t][b]);
+                    if (upper && valid) {        // the y partner lives 64 (conv2) / 32 (conv4) lanes down: park the values
+                        float* dst = stg + (((L == 2 ? t * FM_A + a : a) * (L == 2 ? 2 : 1) + (x >> 1)) * N + h * (N / 2) + 16 * b + 8 * odd);
+                        *reinterpret_cast<float4*>(dst) = make_float4(cv[t][b][0], cv[t][b][1], cv[t][b][2], cv[t][b][3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(cv[t][b][4], cv[t][b][5], cv[t][b][6], cv[t][b][7]);
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cv[t][b][i] = u[i];
                 }
             }
             if (valid) atomicMax(&ms->amax[L][a], __float_as_uint(mx));
         }
     }
+    tcgen05_fence_before();
     fm_epi_sync();
-    // ---- pass 2
-    const bool writer = POOL ? ((L == 2) ? (q < 2) : (q == 0)) : rows_here;
+    const bool writer = POOL ? (rows_here && !upper) : rows_here;
     if (writer) {
-#pragma unroll 1
+#pragma unroll
         for (int t = 0; t < TILES; ++t) {
             const int r = t * 128 + l;
             const int y = r / AW, a = (r % AW) / WP, x = r % WP;
-            const bool valid = y < HO && x < HO && a < na && (!POOL || !(x & 1));
-            const float inv = (L == 1) ? ms->inv1[a] : fm_pow2(-fm_scale_exp(ms->amax[L - 1][a]));
+            const bool valid = y < HO && x < HO && a < na;
             const float mul = fm_pow2(fm_scale_exp(ms->amax[L][a]));
             int orow;
             if (LO == 5) orow = a;
             else if (POOL) orow = ((y >> 1) + 1) * OAW + a * OWP + (x >> 1) + 1;
             else orow = (y + 1) * OAW + a * OWP + x + 1;
-#pragma unroll 1
-            for (int b = 0; b < NB; ++b) {
-                const int c0 = h * (N / 2) + 16 * b;
-                float u[16];
-                fm_row_vals<L>(tmem_lane, t, c0, inv, cst, u);
-                if (POOL) {
+            if (valid) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) u[i] = fmaxf(u[i], __shfl_down_sync(0xffffffffu, u[i], 1));
-                    if (valid) {
-                        const float* src = stg + (((L == 2 ? t * FM_A + a : a) * (L == 2 ? 2 : 1) + (x >> 1)) * N + c0);
+                for (int b = 0; b < NB; ++b) {
+                    const int c0 = h * (N / 2) + 16 * b;
+                    if constexpr (POOL) {
+                        const float* src = stg + (((L == 2 ? t * FM_A + a : a) * (L == 2 ? 2 : 1) + (x >> 1)) * N + c0 + 8 * odd);
+                        const float4 p0 = fm_lds4(src), p1 = fm_lds4(src + 4);
+                        float p[8];
+                        p[0] = fmaxf(cv[t][b][0], p0.x); p[1] = fmaxf(cv[t][b][1], p0.y);
+                        p[2] = fmaxf(cv[t][b][2], p0.z); p[3] = fmaxf(cv[t][b][3], p0.w);
+                        p[4] = fmaxf(cv[t][b][4], p1.x); p[5] = fmaxf(cv[t][b][5], p1.y);
+                        p[6] = fmaxf(cv[t][b][6], p1.z); p[7] = fmaxf(cv[t][b][7], p1.w);
+                        fm_store8(sm_base + OUT, OLBO, OPL, orow, (c0 >> 3) + odd, p, mul);
+                    } else {
+                        float p[8];
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 p = *reinterpret_cast<const float4*>(src + i);
-                            u[i] = fmaxf(u[i], p.x); u[i + 1] = fmaxf(u[i + 1], p.y);
-                            u[i + 2] = fmaxf(u[i + 2], p.z); u[i + 3] = fmaxf(u[i + 3], p.w);
+                        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) p[i] = cv[t][b][8 * hh + i];
+                            fm_store8(sm_base + OUT, OLBO, OPL, orow, (c0 >> 3) + hh, p, mul);
                         }
                     }
                 }
-                if (valid) fm_store16(sm_base + OUT, OLBO, OPL, orow, c0, u, mul);
             }
         }
     }
-    tcgen05_fence_before();
     fence_proxy_async_smem();
     fm_arrive_warp(&ms->act_ready);
+    FM_ACC(26 + L);
 }
 
 // =====================================================================================================================
@@ -401,11 +455,19 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(&ms->tmem_slot);
+    {   // epilogue constants (weights: never produced by the kernel in front of this one)
+        float* cs = reinterpret_cast<float*>(sm + FM_CST);
+        for (int i = threadIdx.x; i < FM_NL * 2 * 128; i += FM_THREADS) cs[i] = __ldg(A.consts + i);
+    }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = ms->tmem_slot;
     const float* __restrict__ cst = A.consts;
+    const bool timing = A.timing != nullptr && blockIdx.x == 0;
+    unsigned long long tacc[40];
+#pragma unroll
+    for (int i = 0; i < 40; ++i) tacc[i] = 0;
     griddep_launch_dependents();       // the next kernel of the stream may start its prologue; it still waits for this grid
 
     if (warp == 1) {
@@ -452,54 +514,89 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
     } else if (warp == 0) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t g = 0, gp = 0, gr = 0;
+            uint32_t gp = 0, gr = 0;
+            FmIssue is;
+            is.sm16 = sm_base >> 4; is.tmem = tmem; is.slot = 0; is.phase = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < A.num_tiles; tile += gridDim.x, ++it) {
                 // ---- conv0: five pairs of image rows, accumulators double-buffered in TMEM columns [256, 512)
-                fm_wait(&ms->act_ready, gr & 1, 50);
+                {
+                    FM_T0();
+                    fm_wait(&ms->act_ready, gr & 1, 50);
+                    FM_ACC(0);
+                }
                 ++gr;
                 tcgen05_fence_after();
                 const uint32_t has_lo = *reinterpret_cast<volatile uint32_t*>(&ms->xflag[it & 1]);
                 {
-                    const uint32_t slot = g % FM_SLOTS, use = g / FM_SLOTS;
-                    fm_wait(&ms->w_full[slot], use & 1, 10 + slot);
+                    {
+                        FM_T0();
+                        fm_wait(&ms->w_full[is.slot], is.phase, 10 + is.slot);
+                        FM_ACC(6);
+                    }
                     tcgen05_fence_after();
-                    const uint32_t bslot = sm_base + FM_RING + slot * FM_SLOT_BYTES;
+                    FM_T0();
+                    const uint32_t a_hi = is.sm16 + (FM_R1 >> 4) + fm_lbo_field(2048);
+                    const uint32_t a_lo = a_hi + (fm_lbo(0) >> 4);
+                    const uint32_t bs = is.sm16 + ((FM_RING + is.slot * FM_SLOT_BYTES) >> 4) + fm_lbo_field(512);
                     for (int j = 0; j < 5; ++j, ++gp) {
                         const uint32_t b = gp & 1;
                         if (gp >= 2) {
+                            const long long tw = timing ? clock64() : 0;
                             fm_wait(&ms->acc0_free[b], ((gp >> 1) - 1) & 1, 52 + b);
+                            if (timing) tacc[32] += (unsigned long long)(clock64() - tw);
                             tcgen05_fence_after();
                         }
+                        if (!has_lo) {
 #pragma unroll
-                        for (int tt = 0; tt < 2; ++tt) {
-                            const int y = 2 * j + tt;
-                            const uint32_t d = tmem + 256 + b * 128 + tt * 64;
+                            for (int tt = 0; tt < 2; ++tt) {
+                                const uint32_t arow = (uint32_t)((2 * j + tt) * 128);       // 16-byte units = rows
+                                const uint32_t d = tmem + 256 + b * 64 + tt * 32;
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx)
+                                for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                                for (int pr = 0; pr < 2; ++pr) {
-                                    const uint32_t aoff = (uint32_t)(((y + 2 * pr) * 128 + kx) * 16);
-                                    const uint64_t db = fm_desc(bslot + (kx * 2 + pr) * 2048, 1024, 128);
-                                    fm_mma(d, fm_desc(sm_base + FM_R1 + aoff, 2048, 128), db, umma_idesc_f16(128, 64),
-                                           (kx | pr) != 0);
-                                    if (has_lo)
-                                        fm_mma(d, fm_desc(sm_base + FM_R1 + fm_lbo(0) + aoff, 2048, 128), db,
-                                               umma_idesc_f16(128, 32), 1);
-                                }
+                                    for (int pr = 0; pr < 2; ++pr)
+                                        fm_mma(d, fm_desc_w(a_hi + arow + (uint32_t)(2 * pr * 128 + kx)),
+                                               fm_desc_w(bs + (((kx * 2 + pr) * 1024) >> 4)), umma_idesc_f16(128, 32), (kx | pr) != 0);
+                            }
+                        } else {
+#pragma unroll
+                            for (int tt = 0; tt < 2; ++tt) {
+                                const uint32_t arow = (uint32_t)((2 * j + tt) * 128);
+                                const uint32_t d = tmem + 256 + b * 64 + tt * 32;
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                                    for (int pr = 0; pr < 2; ++pr) {
+                                        const uint32_t aoff = arow + (uint32_t)(2 * pr * 128 + kx);
+                                        const uint64_t db = fm_desc_w(bs + (((kx * 2 + pr) * 1024) >> 4));
+                                        fm_mma(d, fm_desc_w(a_hi + aoff), db, umma_idesc_f16(128, 32), (kx | pr) != 0);
+                                        fm_mma(d, fm_desc_w(a_lo + aoff), db, umma_idesc_f16(128, 32), 1);
+                                    }
+                            }
                         }
-                        umma_commit(&ms->acc0_full[b]);
+                        fm_commit(&ms->acc0_full[b]);
                     }
-                    umma_commit(&ms->w_free[slot]);
-                    ++g;
+                    fm_commit(&ms->w_free[is.slot]);
+                    if (++is.slot == FM_SLOTS) { is.slot = 0; is.phase ^= 1; }
+                    FM_ACC(12);
                 }
 #define FM_ISSUE(Lx)                                   \
-    fm_wait(&ms->act_ready, gr & 1, 50 + Lx);          \
+    {                                                  \
+        FM_T0();                                       \
+        fm_wait(&ms->act_ready, gr & 1, 50 + Lx);      \
+        FM_ACC(Lx);                                    \
+    }                                                  \
     ++gr;                                              \
     tcgen05_fence_after();                             \
-    fm_issue_layer<Lx>(sm_base, tmem, ms, g);
+    fm_issue_layer<Lx>(is, ms, timing, tacc);
                 FM_ISSUE(1) FM_ISSUE(2) FM_ISSUE(3) FM_ISSUE(4) FM_ISSUE(5)
 #undef FM_ISSUE
+                tacc[18] += 1;
+            }
+            if (timing) {
+                for (int i = 0; i < 19; ++i) atomicAdd(&A.timing[i], tacc[i]);
+                atomicAdd(&A.timing[32], tacc[32]);
             }
         }
     } else {
@@ -514,11 +611,19 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
             const int na = min(FM_A, A.total_agents - tile * FM_A);
             const bool bulk = A.x_bulk && na == FM_A;
             // ---- inputs: per-agent scale, fp16 split into the padded in0 planes
+            const long long t_conv0 = timing ? clock64() : 0;
             if (et < FM_NL * FM_A) (&ms->amax[0][0])[et] = 0;
             if (et == 64) ms->xflag[(it + 1) & 1] = 0;
             fm_zero(sm_base + FM_R2, 2 * fm_planes(1) * fm_lbo(1), et);       // act1 borders
             fm_wait_warp(&ms->xraw_full, it & 1, 41);
-            const float* xs = bulk ? reinterpret_cast<const float*>(sm + FM_XRAW) : A.x + (size_t)tile * FM_A * 363;
+            const float* xs = reinterpret_cast<const float*>(sm + FM_XRAW);
+            if (!bulk) {
+                // ragged last tile, unaligned or host-mapped inputs: one coalesced pass of plain loads into the same buffer
+                const float* xg = A.x + (size_t)tile * FM_A * 363;
+                float* xw = reinterpret_cast<float*>(sm + FM_XRAW);
+                for (int i = et; i < na * 363; i += FM_EPI_THREADS) xw[i] = __ldg(xg + i);
+                fm_epi_sync();
+            }
             {
                 const int a = ew;      // one warp per agent
                 float m = 0.f;
@@ -549,7 +654,10 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
                         const __half2 h01 = __floats2half2_rn(v0, v1), h2 = __floats2half2_rn(v2, 0.f);
                         const float2 f01 = __half22float2(h01), f2 = __half22float2(h2);
                         const __half2 l01 = __floats2half2_rn(v0 - f01.x, v1 - f01.y), l2 = __floats2half2_rn(v2 - f2.x, 0.f);
-                        hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h2);
+                        // K slot of a pixel: [x0 x1 x2 | x0 x1 x2 | 0 0] -- the filter image holds W_hi in the first triple and
+                        // W_lo in the second, so one MMA accumulates x_hi * (W_hi + W_lo)
+                        const uint32_t w01 = *reinterpret_cast<const uint32_t*>(&h01), w2 = *reinterpret_cast<const uint32_t*>(&h2);
+                        hi.x = w01; hi.y = (w2 & 0xFFFFu) | (w01 << 16); hi.z = (w01 >> 16) | (w2 << 16);
                         lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l2);
                         any_lo |= (lo.x | lo.y) & 0x7FFF7FFFu;
                     }
@@ -562,58 +670,75 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
             fm_arrive_warp(&ms->xraw_free);
             fm_epi_sync();                     // xflag / act1 zeroes / in0 complete in every warp
             fm_arrive_warp(&ms->act_ready);
+            if (timing) tacc[19] += (unsigned long long)(clock64() - t_conv0);
 
             // ---- conv0 epilogue: y pairs are the two accumulators of a pair, x pairs neighbouring lanes
             {
-                const int a = l >> 4, x = l & 15;
+                const int a = l >> 4, x = l & 15, odd = lane & 1;
                 const float inv = ms->inv0[a], mul = ms->mul1[a];
                 const int c0 = h * 16;
+                const float* cs = reinterpret_cast<const float*>(sm + FM_CST) + c0;
+                float k[16], sh[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 s4 = fm_lds4(cs + i), t4 = fm_lds4(cs + 128 + i);
+                    k[i] = s4.x * inv; k[i + 1] = s4.y * inv; k[i + 2] = s4.z * inv; k[i + 3] = s4.w * inv;
+                    sh[i] = t4.x; sh[i + 1] = t4.y; sh[i + 2] = t4.z; sh[i + 3] = t4.w;
+                }
+                const bool valid = (x & ~1) < 10 && a < na;
+                const int orow0 = fm_aw(1) + a * fm_wp(1) + (x >> 1) + 1;
                 for (int j = 0; j < 5; ++j, ++gpe) {
                     const uint32_t b = gpe & 1;
-                    fm_wait_warp(&ms->acc0_full[b], (gpe >> 1) & 1, 60 + b);
+                    {
+                        FM_T0();
+                        fm_wait_warp(&ms->acc0_full[b], (gpe >> 1) & 1, 60 + b);
+                        FM_ACC(20);
+                    }
                     tcgen05_fence_after();
-                    const uint32_t col = 256 + b * 128 + c0;
-                    float p0[16], p1[16], q0[16], q1[16];
+                    FM_T0();
+                    const uint32_t col = 256 + b * 64 + c0;
+                    float p0[16], q0[16];
                     fm_tmem_ld16(tmem_lane + col, p0);
-                    fm_tmem_ld16(tmem_lane + col + 32, p1);
-                    fm_tmem_ld16(tmem_lane + col + 64, q0);
-                    fm_tmem_ld16(tmem_lane + col + 96, q1);
+                    fm_tmem_ld16(tmem_lane + col + 32, q0);
                     fm_tmem_wait_ld();
                     tcgen05_fence_before();
                     fm_arrive_warp(&ms->acc0_free[b]);
+                    if (timing) tacc[33] += (unsigned long long)(clock64() - _t0);
                     float u[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float sc = __ldg(cst + c0 + i), sh = __ldg(cst + 128 + c0 + i);
-                        const float u0 = fmaf((p0[i] + p1[i]) * inv, sc, sh), u1 = fmaf((q0[i] + q1[i]) * inv, sc, sh);
-                        float m = fmaxf(fmaxf(u0, u1), 0.f);
-                        u[i] = fmaxf(m, __shfl_down_sync(0xffffffffu, m, 1));
-                    }
-                    if (x < 10 && !(x & 1) && a < na)
-                        fm_store16(sm_base + FM_R2, fm_lbo(1), fm_planes(1), (j + 1) * fm_aw(1) + a * fm_wp(1) + (x >> 1) + 1,
-                                   c0, u, mul);
+                    for (int i = 0; i < 16; ++i)
+                        u[i] = fmaxf(fmaxf(fmaf(p0[i], k[i], sh[i]), fmaf(q0[i], k[i], sh[i])), 0.f);
+                    float pp[8];
+                    fm_xpool(u, odd, pp);
+                    if (valid) fm_store8(sm_base + FM_R2, fm_lbo(1), fm_planes(1), orow0 + j * fm_aw(1), (c0 >> 3) + odd, pp, mul);
+                    FM_ACC(26);
                 }
                 fence_proxy_async_smem();
                 fm_arrive_warp(&ms->act_ready);
             }
-            fm_epilogue_dyn<1>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
-            fm_epilogue_dyn<2>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
-            fm_epilogue_dyn<3>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
-            fm_epilogue_dyn<4>(sm, sm_base, tmem_lane, ms, cst, na, q, h, lane, et, gl);
+            fm_epilogue_dyn<1>(sm, sm_base, tmem_lane, ms, na, q, h, lane, et, gl, timing, tacc);
+            fm_epilogue_dyn<2>(sm, sm_base, tmem_lane, ms, na, q, h, lane, et, gl, timing, tacc);
+            fm_epilogue_dyn<3>(sm, sm_base, tmem_lane, ms, na, q, h, lane, et, gl, timing, tacc);
+            fm_epilogue_dyn<4>(sm, sm_base, tmem_lane, ms, na, q, h, lane, et, gl, timing, tacc);
             // ---- compress MLP: rows 0..7 of the tile are the agents
-            fm_wait_warp(&ms->layer_full, gl & 1, 35);
+            {
+                FM_T0();
+                fm_wait_warp(&ms->layer_full, gl & 1, 35);
+                FM_ACC(25);
+            }
             ++gl;
             tcgen05_fence_after();
+            const long long t_mlp0 = timing ? clock64() : 0;
             if (q == 0) {
                 const int a = lane & 7;
                 const float inv = fm_pow2(-fm_scale_exp(ms->amax[4][a]));
-#pragma unroll 1
+                const float* cs = reinterpret_cast<const float*>(sm + FM_CST) + 5 * 256 + h * 64;
+#pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int c0 = h * 64 + 16 * b;
                     float u[16];
-                    fm_row_vals<5>(tmem_lane, 0, c0, inv, cst, u);
+                    fm_block_vals<5>(tmem_lane + h * 64 + 16 * b, cs + 16 * b, inv, u);
                     if (lane < 8 && a < na) {
-                        float* dst = A.feat + (size_t)(tile * FM_A + a) * 128 + c0;
+                        float* dst = A.feat + (size_t)(tile * FM_A + a) * 128 + h * 64 + 16 * b;
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
                             *reinterpret_cast<float4*>(dst + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
@@ -622,7 +747,11 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
             }
             tcgen05_fence_before();
             fm_epi_sync();      // every warp is done with this tile's shared state before the next tile resets it
+            if (timing) tacc[31] += (unsigned long long)(clock64() - t_mlp0);
         }
+        if (timing && warp == 4 && lane == 0)          // warp 4 = quadrant 0, channel half 0: has work in every layer
+            for (int i = 19; i < 40; ++i)
+                if (i != 32) atomicAdd(&A.timing[i], tacc[i]);
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -656,14 +785,14 @@ __global__ void fm_prep_image_kernel(const float* __restrict__ w, __half* __rest
     float v = 0.f;
     int islo = 0;
     if (L == 0) {
-        // [kx][pr][plane][n2 (64 = hi | lo)][8]
+        // [kx][pr][plane][n (32)][8]: halves 0-2 = W_hi of input channel e, 3-5 = W_lo of channel e-3
         int r = idx >> 3;
-        const int n2 = r & 63; r >>= 6;
+        const int n = r & 31; r >>= 5;
         const int p = r & 1; r >>= 1;
         const int pr = r & 1, kx = r >> 1;
-        const int ky = 2 * pr + p, n = n2 & 31;
-        islo = n2 >> 5;
-        if (ky < 3 && e < 3) v = w[(n * 3 + e) * 9 + ky * 3 + kx];
+        const int ky = 2 * pr + p;
+        islo = e >= 3;
+        if (ky < 3 && e < 6) v = w[(n * 3 + (e % 3)) * 9 + ky * 3 + kx];
     } else if (L <= 3) {
         // [unit][plane][n2 (2N = hi | lo)][8]
         const int Cin = fm_planes(L) * 8, KS = fm_ks(L);
@@ -763,8 +892,8 @@ static unsigned long long* g_fm_timing = nullptr;
 int debug_feature_mma_timing(unsigned long long* out32) {
     if (!g_fm_timing) return GPP_ERR_INVALID;
     cudaDeviceSynchronize();
-    cudaMemcpy(out32, g_fm_timing, 256, cudaMemcpyDeviceToHost);
-    cudaMemset(g_fm_timing, 0, 256);
+    cudaMemcpy(out32, g_fm_timing, 320, cudaMemcpyDeviceToHost);
+    cudaMemset(g_fm_timing, 0, 320);
     return GPP_OK;
 }
 
@@ -780,7 +909,7 @@ int launch_feature_mma_kernel(const FeArgs& fa, const float* arena, int x_bulk, 
     a.pdl = fa.pdl;
     a.timing = nullptr;
     if (debug_option(DBG_TC_TIMING)) {
-        if (!g_fm_timing) { cudaMalloc(&g_fm_timing, 256); cudaMemset(g_fm_timing, 0, 256); }
+        if (!g_fm_timing) { cudaMalloc(&g_fm_timing, 320); cudaMemset(g_fm_timing, 0, 320); }
         a.timing = g_fm_timing;
     }
     static SmemConfig smem_cfg;

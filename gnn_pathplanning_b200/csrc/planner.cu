@@ -269,6 +269,7 @@ extern "C" int gpp_planner_set_graph_filter_mode(gpp_planner* p, int mode) {
 // debug: per-layer {staging loop, wait for MMAs, epilogue} cycle totals of feature_tc_kernel + tiles at [18]
 extern "C" int gpp_debug_feature_tc_timing(unsigned long long* out20) { return debug_feature_tc_timing(out20); }
 extern "C" int gpp_debug_feature_timing(unsigned long long* out7) { return debug_feature_timing(out7); }
+extern "C" int gpp_debug_feature_mma_timing(unsigned long long* out32) { return debug_feature_mma_timing(out32); }
 
 // debug switches (include/gnnpp_b200_debug.h)
 extern "C" int gpp_debug_set_option(const char* name, int value) {
@@ -508,9 +509,9 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         GPP_CUDA_OK(cudaEventRecord(e0, st));
     }
     int rc;
-    // auto = the register-tiled CUDA-core kernel at every size: it is 5-10 % faster than the tcgen05 kernel even at
-    // 40,960 agents per launch (profiles/r01_planner_microbench.txt); the tcgen05 kernel runs on request only
-    if (p->fe_mode == 3) {
+    // auto = the im2col-free fp16-split tcgen05 kernel: 41 vs 50 us at 640 agents, 1.25 vs 2.0 ms at 40,960
+    // (profiles/r02_fe_microbench.txt); the CUDA-core and 3xTF32 kernels run on request
+    if (p->fe_mode == 3 || p->fe_mode == 0) {
         rc = launch_feature_mma_kernel(fa, A + p->off_fmma, allow_bulk, st);
     } else if (p->fe_mode == 2) {
         const float* imgs[6];

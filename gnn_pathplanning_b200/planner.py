@@ -353,7 +353,8 @@ class DecentralPlannerNet(nn.Module):
         self.__dict__["_gf_mode"] = {"auto": 0, "cuda": 1, "tc": 2, "pair": 3}[mode]
 
     def set_feature_mode(self, mode: str) -> None:
-        """Feature extractor kernel: 'auto' (default), 'cuda' (fp32 CUDA cores) or 'tc' (tcgen05 3xTF32)."""
+        """Feature extractor kernel: 'auto' (default = 'mma'), 'mma' (tcgen05, fp16 2-way split, im2col-free), 'cuda'
+        (fp32 CUDA cores) or 'tc' (tcgen05 3xTF32 implicit GEMM)."""
         self.__dict__["_fe_mode"] = {"auto": 0, "cuda": 1, "tc": 2, "mma": 3}[mode]
 
     def _forward_fused(self, x, S):

@@ -37,6 +37,11 @@ int gpp_debug_gf_timing(unsigned long long* out6);
 /* Same for the tcgen05 feature extractor: [3*L + {0,1,2}] = layer L staging loop / wait for MMAs / epilogue,
  * [18] = agent tiles (thread 0 of every CTA). */
 int gpp_debug_feature_tc_timing(unsigned long long* out20);
+/* feature_mma_kernel phase timers of block 0 ("tc_timing" option on): [0..5] MMA warp waiting for a layer's input,
+ * [6..11] waiting for filter chunks, [12..17] issuing, [18] tiles, [19] input conversion, [20..25] epilogue waiting for
+ * accumulators, [26..31] epilogue work, [32] conv0 MMA waiting for a free accumulator pair, [33] conv0 epilogue TMEM
+ * loads; 40 entries; cycles, cleared by the call */
+int gpp_debug_feature_mma_timing(unsigned long long* out40);
 /* Block 0 of the CUDA-core feature extractor ("fe_timing"): input staging, conv0, conv1,
  * conv2, conv3, conv4, compress MLP + store. */
 int gpp_debug_feature_timing(unsigned long long* out7);

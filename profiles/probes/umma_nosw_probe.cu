@@ -94,6 +94,50 @@ __global__ void __launch_bounds__(128) probe(const __half* a_g, const __half* b_
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
 }
 
+// conv0-like issue pattern: one A plane of 1664 rows (LBO = 2048 B = the next image row of the tile), six (kx, pr) taps,
+// two M tiles, N = 32, accumulators at columns 0 and 32 -- timing only
+__global__ void __launch_bounds__(128) probe_conv0(long long* cyc, int reps, int lbo_bytes, int ncols) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    __half* sa = reinterpret_cast<__half*>(sm);                        // 1664 + 512 rows * 16 B
+    __half* sb = reinterpret_cast<__half*>(sm + 2176 * 16);            // 6 * 2 * 32 * 16 B = 6 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 2176 * 16 + 6144);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    for (int i = threadIdx.x; i < 2176 * 8; i += 128) sa[i] = __float2half((float)(i % 3));
+    for (int i = threadIdx.x; i < 6144 / 2; i += 128) sb[i] = __float2half((float)(i % 5));
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r)
+            for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int pr = 0; pr < 2; ++pr) {
+                        const uint32_t arow = (uint32_t)(((r % 5) * 2 + tt + 2 * pr) * 128 + kx);
+                        mma(tmem + tt * ncols, desc_nosw(smem_u32(sa) + arow * 16, lbo_bytes, 128),
+                            desc_nosw(smem_u32(sb) + (kx * 2 + pr) * 1024, 512, 128), idesc_f16(128, 32), (kx | pr) != 0);
+                    }
+        commit(bar);
+        mbar_wait(bar, 0);
+        cyc[0] = clock64() - t0;
+    }
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
 int main() {
     std::vector<__half> a(2 * ROWS * 8), b(2 * 128 * 8);
     std::vector<float> af(a.size()), bf(b.size());
@@ -134,6 +178,18 @@ int main() {
         cudaDeviceSynchronize();
         long long c; cudaMemcpy(&c, cg, 8, cudaMemcpyDeviceToHost);
         printf("N=%3d reps=%3d cycles=%lld per_mma=%.1f\n", N, reps, c, (double)c / reps);
+    }
+    {
+        const int smem2 = 2176 * 16 + 6144 + 64;
+        cudaFuncSetAttribute(probe_conv0, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+        for (int lbo : {2048, 2064, 6272, 8192})
+            for (int ncols : {32, 64}) {
+                probe_conv0<<<1, 128, smem2>>>(cg, 20, lbo, ncols);
+                cudaError_t e = cudaDeviceSynchronize();
+                long long c; cudaMemcpy(&c, cg, 8, cudaMemcpyDeviceToHost);
+                printf("conv0-like: LBO=%5d acc spacing=%2d cols: %s, %.1f cycles per MMA (240 MMAs)\n", lbo, ncols,
+                       cudaGetErrorString(e), (double)c / 240.0);
+            }
     }
     printf(bad_total ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad_total != 0;
