@@ -455,10 +455,6 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc<512>(&ms->tmem_slot);
-    {   // epilogue constants (weights: never produced by the kernel in front of this one)
-        float* cs = reinterpret_cast<float*>(sm + FM_CST);
-        for (int i = threadIdx.x; i < FM_NL * 2 * 128; i += FM_THREADS) cs[i] = __ldg(A.consts + i);
-    }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -615,6 +611,11 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
             if (et < FM_NL * FM_A) (&ms->amax[0][0])[et] = 0;
             if (et == 64) ms->xflag[(it + 1) & 1] = 0;
             fm_zero(sm_base + FM_R2, 2 * fm_planes(1) * fm_lbo(1), et);       // act1 borders
+            if (it == 0) {   // epilogue constants (weights: never produced by the kernel in front of this one); their latency
+                             // hides behind the first input tile's
+                float* cs = reinterpret_cast<float*>(sm + FM_CST);
+                for (int i = et; i < FM_NL * 2 * 128; i += FM_EPI_THREADS) cs[i] = __ldg(A.consts + i);
+            }
             fm_wait_warp(&ms->xraw_full, it & 1, 41);
             const float* xs = reinterpret_cast<const float*>(sm + FM_XRAW);
             if (!bulk) {
@@ -625,31 +626,29 @@ __global__ void __launch_bounds__(FM_THREADS, 1) feature_mma_kernel(const FmArgs
                 fm_epi_sync();
             }
             {
-                const int a = ew;      // one warp per agent
+                // one warp per agent: scale from max |x|, then the agent's 13 x 16 padded pixels (no barrier in between)
+                const int a = ew;
                 float m = 0.f;
                 if (a < na)
                     for (int i = lane; i < 363; i += 32) m = fmaxf(m, fabsf(xs[a * 363 + i]));
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const int e0 = fm_scale_exp(__float_as_uint(m));
+                const float mul = fm_pow2(e0);
                 if (lane == 0) {
-                    const int e0 = fm_scale_exp(__float_as_uint(m));
-                    ms->mul0[a] = fm_pow2(e0);
+                    ms->mul0[a] = mul;
                     ms->inv0[a] = fm_pow2(-e0);
                     const float bound = m * __ldg(cst + FM_CONST_MISC) + __ldg(cst + FM_CONST_MISC + 1);
                     const int e1 = fm_scale_exp(__float_as_uint(bound));
                     ms->mul1[a] = fm_pow2(e1);
                     ms->inv1[a] = fm_pow2(-e1);
                 }
-            }
-            fm_epi_sync();
-            {
                 uint32_t any_lo = 0;
-                for (int row = et; row < fm_rows(0); row += FM_EPI_THREADS) {
-                    const int y = row >> 7, a = (row >> 4) & 7, x = row & 15;
+                for (int i = lane; i < 13 * 16; i += 32) {
+                    const int y = i >> 4, x = i & 15, row = y * 128 + a * 16 + x;
                     uint4 hi = make_uint4(0, 0, 0, 0), lo = make_uint4(0, 0, 0, 0);
                     if (y >= 1 && y <= 11 && x >= 1 && x <= 11 && a < na) {
                         const float* p = xs + a * 363 + (y - 1) * 11 + (x - 1);
-                        const float mul = ms->mul0[a];
                         const float v0 = p[0] * mul, v1 = p[121] * mul, v2 = p[242] * mul;
                         const __half2 h01 = __floats2half2_rn(v0, v1), h2 = __floats2half2_rn(v2, 0.f);
                         const float2 f01 = __half22float2(h01), f2 = __half22float2(h2);

@@ -509,9 +509,11 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
         GPP_CUDA_OK(cudaEventRecord(e0, st));
     }
     int rc;
-    // auto = the im2col-free fp16-split tcgen05 kernel: 41 vs 50 us at 640 agents, 1.25 vs 2.0 ms at 40,960
-    // (profiles/r02_fe_microbench.txt); the CUDA-core and 3xTF32 kernels run on request
-    if (p->fe_mode == 3 || p->fe_mode == 0) {
+    // auto = the im2col-free fp16-split tcgen05 kernel from 448 agents (more than 3 per SM): 41 vs 50 us at 640 agents,
+    // 1.23 vs 2.0 ms at 40,960 (profiles/r02_fe_microbench.txt).  One of its tiles costs ~33 us however few agents it
+    // holds, the CUDA-core kernel ~18 us + 6.5 us per agent of a tile, so small batches (the batch-1 rollout step) stay
+    // on the CUDA cores.  The 3xTF32 implicit-GEMM kernel runs on request only.
+    if (p->fe_mode == 3 || (p->fe_mode == 0 && rows >= 448)) {
         rc = launch_feature_mma_kernel(fa, A + p->off_fmma, allow_bulk, st);
     } else if (p->fe_mode == 2) {
         const float* imgs[6];

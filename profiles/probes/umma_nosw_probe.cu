@@ -138,6 +138,57 @@ __global__ void __launch_bounds__(128) probe_conv0(long long* cyc, int reps, int
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
 }
 
+// M = 64: where do the 64 accumulator rows land in TMEM, and what does an instruction cost?
+__global__ void __launch_bounds__(128) probe_m64(const __half* a_g, const __half* b_g, float* d_g, int N, long long* cyc, int reps) {
+    extern __shared__ __align__(1024) unsigned char sm[];
+    __half* sa = reinterpret_cast<__half*>(sm);
+    __half* sb = reinterpret_cast<__half*>(sm + 2 * ROWS * 16);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 2 * ROWS * 16 + 4096);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    for (int i = threadIdx.x; i < 2 * ROWS * 8; i += 128) sa[i] = a_g[i];
+    for (int i = threadIdx.x; i < 2 * 128 * 8; i += 128) sb[i] = b_g[i];
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *slot;
+    // poison all 128 lanes first (M=128 MMA of zeros is awkward: just overwrite after reading) -- read-back marks untouched lanes
+    if (threadIdx.x == 0) {
+        const uint64_t da = desc_nosw(smem_u32(sa) + 3 * 16, ROWS * 16, 128);
+        const uint64_t db = desc_nosw(smem_u32(sb), 128 * 16, 128);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) mma(tmem, da, db, idesc_f16(64, N), r > 0 ? 1u : 0u);
+        commit(bar);
+        mbar_wait(bar, 0);
+        cyc[0] = clock64() - t0;
+    }
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int w = threadIdx.x >> 5;
+    {
+        uint32_t r[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(tmem + ((uint32_t)(32 * w) << 16))
+                     : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int i = 0; i < 16; ++i) d_g[(size_t)threadIdx.x * 16 + i] = __uint_as_float(r[i]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+}
+
 int main() {
     std::vector<__half> a(2 * ROWS * 8), b(2 * 128 * 8);
     std::vector<float> af(a.size()), bf(b.size());
@@ -190,6 +241,38 @@ int main() {
                 printf("conv0-like: LBO=%5d acc spacing=%2d cols: %s, %.1f cycles per MMA (240 MMAs)\n", lbo, ncols,
                        cudaGetErrorString(e), (double)c / 240.0);
             }
+    }
+    {
+        cudaFuncSetAttribute(probe_m64, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        probe_m64<<<1, 128, smem>>>(ag, bg, dg, 32, cg, 1);
+        cudaError_t e = cudaDeviceSynchronize();
+        printf("M=64 probe: %s\n", cudaGetErrorString(e));
+        std::vector<float> d(128 * 16);
+        cudaMemcpy(d.data(), dg, d.size() * 4, cudaMemcpyDeviceToHost);
+        // reference rows (shift 3), first 16 columns
+        int lane_of_row[64];
+        for (int m = 0; m < 64; ++m) {
+            lane_of_row[m] = -1;
+            float ref[16];
+            for (int n = 0; n < 16; ++n) {
+                ref[n] = 0.f;
+                for (int k = 0; k < 16; ++k) ref[n] += af[((size_t)(k >> 3) * ROWS + m + 3) * 8 + (k & 7)] * bf[((size_t)(k >> 3) * 128 + n) * 8 + (k & 7)];
+            }
+            for (int l = 0; l < 128; ++l) {
+                bool same = true;
+                for (int n = 0; n < 16; ++n) same = same && d[(size_t)l * 16 + n] == ref[n];
+                if (same) { lane_of_row[m] = l; break; }
+            }
+        }
+        printf("M=64 row -> TMEM lane:");
+        for (int m = 0; m < 64; ++m) printf(" %d", lane_of_row[m]);
+        printf("\n");
+        for (int N : Ns) {
+            probe_m64<<<1, 128, smem>>>(ag, bg, dg, N, cg, 256);
+            cudaDeviceSynchronize();
+            long long c; cudaMemcpy(&c, cg, 8, cudaMemcpyDeviceToHost);
+            printf("M=64 N=%3d: %.1f cycles per MMA\n", N, (double)c / 256);
+        }
     }
     printf(bad_total ? "PROBE FAILED\n" : "PROBE OK\n");
     return bad_total != 0;

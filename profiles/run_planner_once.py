@@ -1,4 +1,4 @@
-"""A few C2-sized planner forwards (for ncu captures of feature_kernel / gf_fwd_kernel)."""
+"""A few planner forwards (for ncu captures).  usage: run_planner_once.py [B N gf_mode fe_mode]"""
 import sys
 sys.path.insert(0, "/root/repo")
 import torch
@@ -12,7 +12,7 @@ class Cfg:
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 m = gp.DecentralPlannerNet(Cfg(N, 3)).cuda().eval()
-m.set_graph_filter_mode("cuda"); m.set_feature_mode("cuda")
+m.set_graph_filter_mode(sys.argv[3] if len(sys.argv) > 3 else "auto"); m.set_feature_mode(sys.argv[4] if len(sys.argv) > 4 else "auto")
 x, S = synthetic.make_batch(B, N, 20, seed=1)
 xt, St = torch.from_numpy(x).cuda(), torch.from_numpy(S).cuda()
 m.addGSO(St)
