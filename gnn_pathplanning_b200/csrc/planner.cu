@@ -7,6 +7,8 @@
 // plus the one-off parameter re-layout (k-major filters, eval BatchNorm folded to scale/shift).
 #include "common.cuh"
 #include "feature.cuh"
+
+#include <utility>
 #include "../../include/gnnpp_b200_debug.h"
 
 #include <stdarg.h>
@@ -145,6 +147,11 @@ struct gpp_planner {
     bool weights_set;
     float* raw;          // device staging for host-provided parameters
     size_t raw_floats;
+    // second compute lane of the pipelined host path (gpp_planner_forward_host_async alternates between two streams
+    // so that the feature kernel of one batch overlaps the graph-filter kernel of the batch before it): its own stream
+    // and scratch; swapped in for the duration of a call by LaneGuard
+    cudaStream_t stream2;
+    float* feat2; size_t feat_rows2; float* gf_lpart2; size_t gf_lpart_rows2; bool pdl_ok2;
     float* feat;         // [rows][128] workspace
     size_t feat_rows;
     const void* alias_host[16];   // pinned host buffers seen by the async entry point and their device aliases
@@ -240,6 +247,9 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->raw);
     cudaFree(p->feat);
     cudaFree(p->gf_lpart);
+    cudaFree(p->feat2);
+    cudaFree(p->gf_lpart2);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
     cudaFree(p->d_x);
     cudaFree(p->d_S);
     cudaFree(p->d_logits);
@@ -361,6 +371,7 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
         int rc0 = order_after_previous_stream(p, st);
         if (rc0) return rc0;
     }
+    if (p->stream2) GPP_CUDA_OK(cudaStreamSynchronize(p->stream2));    // batches in flight on the second lane read the arena
     gpp_planner_weights d = *w;
     const int K = p->K;
     if (!on_device) {
@@ -425,6 +436,7 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     if (rc) return rc;
     rc = launch_split_taps(A + p->off_gfw, A + p->off_gfws, K * 128, st);
     p->pdl_ok = false;
+    p->pdl_ok2 = false;
     if (rc) return rc;
     rc = launch_prep_umma_taps(d.gf_w, A + p->off_gfimg, K, st);
     if (rc) return rc;
@@ -476,11 +488,24 @@ static int ensure_gf_scratch(gpp_planner* p, size_t rows, cudaStream_t st) {
 
 // x / S / logits may be device memory or pinned host memory mapped into the device address space
 // (zero-copy); `allow_bulk` = 0 keeps the filter kernel off the bulk-copy engine for host-mapped S.
+struct LaneGuard {       // lane 1: the handle's scratch fields point at the second lane's buffers inside the call
+    gpp_planner* p;
+    bool on;
+    void swap_in_out() {
+        std::swap(p->feat, p->feat2); std::swap(p->feat_rows, p->feat_rows2);
+        std::swap(p->gf_lpart, p->gf_lpart2); std::swap(p->gf_lpart_rows, p->gf_lpart_rows2);
+        std::swap(p->pdl_ok, p->pdl_ok2);
+    }
+    LaneGuard(gpp_planner* pl, int lane) : p(pl), on(lane != 0) { if (on) swap_in_out(); }
+    ~LaneGuard() { if (on) swap_in_out(); }
+};
+
 static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, int s_is_f64,
                                 float* logits, float* features_out, int B, int N, int allow_bulk,
-                                cudaStream_t st) {
+                                cudaStream_t st, int lane = 0) {
     const size_t rows = (size_t)B * N;
-    {
+    LaneGuard lane_guard(p, lane);
+    if (lane == 0) {       // lane 1's scratch is only ever used on its own stream
         int rc0 = order_after_previous_stream(p, st);
         if (rc0) return rc0;
     }
@@ -621,6 +646,7 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     if (!p->copied[slot]) GPP_CUDA_OK(cudaEventCreateWithFlags(&p->copied[slot], cudaEventDisableTiming));
     if (p->a_x_floats[slot] < nx || p->a_S_bytes[slot] < sb) {
         GPP_CUDA_OK(cudaStreamSynchronize(p->stream));
+        if (p->stream2) GPP_CUDA_OK(cudaStreamSynchronize(p->stream2));
         GPP_CUDA_OK(cudaStreamSynchronize(p->copy_stream));
         if (p->a_x_floats[slot] < nx) {
             cudaFree(p->a_x[slot]); p->a_x[slot] = nullptr; p->a_x_floats[slot] = 0;
@@ -646,13 +672,17 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
         GPP_LAUNCH_CHECK();
     }
     GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));
-    GPP_CUDA_OK(cudaStreamWaitEvent(p->stream, p->copied[slot], 0));
-    // the feature workspace between the two kernels is shared by the calls in flight; they are ordered
-    // on the compute stream, so a later call's feature kernel starts after the earlier filter kernel
+    // two compute lanes (stream + feature workspace + filter scratch each), tickets alternate between them: the batches
+    // are independent, so the feature kernel of ticket t+1 (80 of 148 SMs at the benchmark size) runs next to the
+    // graph-filter kernel of ticket t instead of behind it
+    const int lane = (int)(t & 1);
+    if (lane && !p->stream2) GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
+    cudaStream_t cst = lane ? p->stream2 : p->stream;
+    GPP_CUDA_OK(cudaStreamWaitEvent(cst, p->copied[slot], 0));
     int rc = planner_forward_impl(p, p->a_x[slot], p->a_S[slot], s_is_f64, reinterpret_cast<float*>(ml),
-                                  nullptr, B, N, 1, p->stream);
+                                  nullptr, B, N, 1, cst, lane);
     if (rc) return rc;
-    GPP_CUDA_OK(cudaEventRecord(ev, p->stream));
+    GPP_CUDA_OK(cudaEventRecord(ev, cst));
     p->next_ticket = t + 1;
     *ticket = t;
     return GPP_OK;
