@@ -712,8 +712,9 @@ def main():
             "e2e": {"value": world * agent_steps * K / (e2e_ms * 1e-3), "unit": UNIT, "steps": K, "windows": e2e_R,
                     "h2d_bytes_per_step": bytes_per_batch, "d2h_bytes_per_step": N_AGENTS * BATCH * 5 * 4,
                     "api": "DecentralPlannerNet.infer_host_async/wait -> gpp_planner_forward_host_async (pinned host "
-                           "buffers; inputs staged by a small copy kernel on a second stream while the previous step's "
-                           "kernels run, logits written straight to host), 3 independent episode batches in flight",
+                           "buffers; inputs staged by a small copy kernel on a copy stream, forward on one of two compute "
+                           "lanes so one batch's CNN overlaps the previous batch's graph filter, logits written straight to "
+                           "host), 3 independent episode batches in flight",
                     "sync_value": world * agent_steps * K / (sync_ms * 1e-3), "sync_windows": sync_R,
                     "sync_api": "DecentralPlannerNet.infer_host -> gpp_planner_forward_host, one blocking call per step"},
             "gpu_launches": int(launches_per_window) * R, "gpu_launches_per_step": int(launches_per_window) / K,

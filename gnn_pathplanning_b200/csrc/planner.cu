@@ -151,6 +151,7 @@ struct gpp_planner {
     // so that the feature kernel of one batch overlaps the graph-filter kernel of the batch before it): its own stream
     // and scratch; swapped in for the duration of a call by LaneGuard
     cudaStream_t stream2;
+    bool lanes_active;   // inside gpp_planner_forward_host_async
     float* feat2; size_t feat_rows2; float* gf_lpart2; size_t gf_lpart_rows2; bool pdl_ok2;
     float* feat;         // [rows][128] workspace
     size_t feat_rows;
@@ -520,7 +521,9 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     fa.x = x; fa.feat = feat; fa.total_agents = (int)rows; fa.apt = 0; fa.num_tiles = 0; fa.timing = nullptr;
     // programmatic dependent launch: each kernel's prologue (barriers, filter prefetch) overlaps the tail of the
     // kernel before it; not for the first forward after the weights changed (the prologue reads them)
-    const int pdl = (!debug_option(DBG_NO_PDL) && p->pdl_ok && !p->profiling) ? 1 : 0;
+    // ... and not on the two-lane pipelined host path: a dependent kernel launched early parks its CTAs (and their shared
+    // memory) on the SMs the other lane's kernel should be using (45.0 vs 48.4 us per step, profiles/r02_e2e_lanes.txt)
+    const int pdl = (!debug_option(DBG_NO_PDL) && p->pdl_ok && !p->profiling && !p->lanes_active) ? 1 : 0;
     fa.pdl = pdl;
     fa.w0t = A + p->off_w[0]; fa.w1t = A + p->off_w[1]; fa.w2t = A + p->off_w[2];
     fa.w3t = A + p->off_w[3]; fa.w4t = A + p->off_w[4]; fa.w5t = A + p->off_w[5];
@@ -679,8 +682,10 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     if (lane && !p->stream2) GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
     cudaStream_t cst = lane ? p->stream2 : p->stream;
     GPP_CUDA_OK(cudaStreamWaitEvent(cst, p->copied[slot], 0));
+    p->lanes_active = true;
     int rc = planner_forward_impl(p, p->a_x[slot], p->a_S[slot], s_is_f64, reinterpret_cast<float*>(ml),
                                   nullptr, B, N, 1, cst, lane);
+    p->lanes_active = false;
     if (rc) return rc;
     GPP_CUDA_OK(cudaEventRecord(ev, cst));
     p->next_ticket = t + 1;
