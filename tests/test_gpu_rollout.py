@@ -48,11 +48,12 @@ class Cfg:
         self.num_agents, self.nGraphFilterTaps, self.device = n, k, torch.device("cuda")
 
 
-@pytest.mark.parametrize("N,W,B,maxstep", [(10, 20, 64, 30), (6, 10, 33, 18)])
+@pytest.mark.parametrize("N,W,B,maxstep", [(10, 20, 64, 30), (6, 10, 33, 18), (32, 30, 5, 10), (40, 36, 3, 8)])
 def test_run_loop_with_planner_vs_oracle(N, W, B, maxstep):
     """BatchedRollout.run: B episodes advanced on the device by the CUDA planner (no per-step host copies); the same
     episodes advanced one by one by oracle/sim_oracle.py fed with the same logits; identical trajectories, goal flags
-    and step bookkeeping, incl. the freezing of finished episodes (agents/decentralplannerlocal.py:606-613)."""
+    and step bookkeeping, incl. the freezing of finished episodes (agents/decentralplannerlocal.py:606-613).  N <= 32
+    runs the warp-per-episode move kernel, N = 40 the thread-per-episode one."""
     import gnn_pathplanning_b200 as gp
     from gnn_pathplanning_b200 import synthetic
     from oracle import planner_oracle as po, sim_oracle
