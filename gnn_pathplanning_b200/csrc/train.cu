@@ -153,6 +153,31 @@ __global__ void linear_fwd_kernel(const float* __restrict__ in, const float* __r
     }
 }
 
+// The 128 -> 128 compress layer, one warp per row: lanes split the reduction (coalesced 512-byte reads of a weight row,
+// 4 inputs per lane in registers), butterfly sum, lane o % 32 keeps output o.  The thread-per-output kernel above reads
+// the weight matrix with a 512-byte stride between lanes: 55 us at 640 rows.
+__global__ void __launch_bounds__(256) linear128_fwd_rowwarp_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                    const float* __restrict__ b, float* __restrict__ out,
+                                                                    long long R, int relu) {
+    const long long r = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const float4 xv = *reinterpret_cast<const float4*>(in + r * 128 + 4 * lane);
+    for (int o0 = 0; o0 < 128; o0 += 32) {
+        float keep = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)(o0 + j) * 128 + 4 * lane));
+            float p = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, xv.w * wv.w)));
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+            if (lane == j) keep = p;
+        }
+        const float v = keep + b[o0 + lane];
+        out[r * 128 + o0 + lane] = relu ? fmaxf(v, 0.f) : v;
+    }
+}
+
 // logits[n][b][a] = ba[a] + sum_f shared[(b*N+n)][f] wa[a][f]
 __global__ void action_fwd_kernel(const float* __restrict__ shared, const float* __restrict__ wa,
                                   const float* __restrict__ ba, float* __restrict__ logits, int B, int N) {
@@ -182,23 +207,40 @@ __global__ void action_bwd_input_kernel(const float* __restrict__ dlogits, const
     dshared[i] = acc;
 }
 // dwa[a][f] = sum_r dlogits[r][a] shared[r][f] ; dba[a] = sum_r dlogits[r][a]   (thread per (a,f), one extra per a)
-__global__ void action_bwd_weight_kernel(const float* __restrict__ dlogits, const float* __restrict__ shared,
-                                         float* __restrict__ dwa, float* __restrict__ dba, int B, int N) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 5 * 128) {
-        const int a = i / 128, f = i - a * 128;
-        double acc = 0.0;
-        for (int b = 0; b < B; ++b)
-            for (int n = 0; n < N; ++n)
-                acc += (double)(dlogits[((size_t)n * B + b) * 5 + a] * shared[((size_t)b * N + n) * 128 + f]);
-        dwa[i] = (float)acc;
-    } else if (i < 5 * 128 + 5) {
-        const int a = i - 5 * 128;
-        double acc = 0.0;
-        for (int b = 0; b < B; ++b)
-            for (int n = 0; n < N; ++n) acc += (double)dlogits[((size_t)n * B + b) * 5 + a];
-        dba[a] = (float)acc;
+// Two stages, both fixed-order (deterministic): partial sums over row chunks (products rounded to float and accumulated in
+// double, as the single-thread-per-output version did), then the chunks in order.  The one-thread-per-(a,f) version
+// walked all B*N rows serially: 102 us at 640 rows.
+constexpr int kActChunks = 32;
+__global__ void action_bwd_weight_partial_kernel(const float* __restrict__ dlogits, const float* __restrict__ shared,
+                                                 double* __restrict__ partial, int B, int N) {
+    const int f = threadIdx.x, chunk = blockIdx.x;          // 128 threads, kActChunks blocks
+    const int M = B * N, per = (M + kActChunks - 1) / kActChunks;
+    const int r0 = chunk * per, r1 = min(M, r0 + per);
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, accb[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int r = r0; r < r1; ++r) {                        // r = b * N + n: the order of the reference's row-major sum
+        const int b = r / N, n = r - b * N;
+        const float* dl = dlogits + ((size_t)n * B + b) * 5;
+        const float sv = shared[(size_t)r * 128 + f];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            acc[a] += (double)(dl[a] * sv);
+            accb[a] += (double)dl[a];
+        }
     }
+#pragma unroll
+    for (int a = 0; a < 5; ++a) partial[((size_t)chunk * 6 + a) * 128 + f] = acc[a];
+    if (f < 5) partial[((size_t)chunk * 6 + 5) * 128 + f] = accb[f];
+}
+__global__ void action_bwd_weight_reduce_kernel(const double* __restrict__ partial, float* __restrict__ dwa,
+                                                float* __restrict__ dba) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;    // 6 * 128 threads: (a, f), a == 5: the bias sums
+    if (i >= 6 * 128) return;
+    const int a = i / 128, f = i - a * 128;
+    if (a == 5 && f >= 5) return;
+    double acc = 0.0;
+    for (int c = 0; c < kActChunks; ++c) acc += partial[((size_t)c * 6 + a) * 128 + f];
+    if (a < 5) dwa[a * 128 + f] = (float)acc;
+    else dba[f] = (float)acc;
 }
 
 // g[i] *= (y[i] > 0)
@@ -774,7 +816,7 @@ extern "C" int gpp_planner_train_forward(const gpp_planner_weights* w, const gpp
             in = a;
         }
     }
-    linear_fwd_kernel<<<grid_for((long long)M * 128), 256, 0, st>>>(in, w->compress_w, w->compress_b, ws + L.feat, M, 128, 128, 1);
+    linear128_fwd_rowwarp_kernel<<<(M + 7) / 8, 256, 0, st>>>(in, w->compress_w, w->compress_b, ws + L.feat, M, 1);
     GPP_LAUNCH_CHECK();
     int rc = gpp_graph_filter_forward(ws + L.feat, S, s_is_f64, w->gf_w, w->gf_b, ws + L.shared, B, N, 128, 128, K,
                                       GPP_NODE_MAJOR, GPP_NODE_MAJOR, 1, ws + L.gf_fwd, stream);
@@ -796,8 +838,13 @@ extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const fl
     // ---- action MLP
     action_bwd_input_kernel<<<grid_for((long long)M * 128), 256, 0, st>>>(dlogits, w->action_w, ws + L.dshared, B, N);
     GPP_LAUNCH_CHECK();
-    action_bwd_weight_kernel<<<(5 * 128 + 5 + 127) / 128, 128, 0, st>>>(dlogits, ws + L.shared, g->action_w, g->action_b, B, N);
-    GPP_LAUNCH_CHECK();
+    {
+        double* apart = reinterpret_cast<double*>(ws + L.partial);      // free until the weight-gradient kernels below
+        action_bwd_weight_partial_kernel<<<kActChunks, 128, 0, st>>>(dlogits, ws + L.shared, apart, B, N);
+        GPP_LAUNCH_CHECK();
+        action_bwd_weight_reduce_kernel<<<6, 128, 0, st>>>(apart, g->action_w, g->action_b);
+        GPP_LAUNCH_CHECK();
+    }
     // ---- graph filter (+ReLU): fused kernels
     int rc = gpp_graph_filter_backward(ws + L.dshared, ws + L.shared, ws + L.feat, S, s_is_f64, w->gf_w, ws + L.dfeat,
                                        g->gf_w, g->gf_b, B, N, 128, 128, K, GPP_NODE_MAJOR, GPP_NODE_MAJOR, 1,

@@ -12,5 +12,5 @@ tt = torch.from_numpy(synthetic.random_targets(64, 10, seed=4)).cuda()
 xt, St = torch.from_numpy(x).cuda(), torch.from_numpy(S).cuda()
 m = gp.DecentralPlannerNet(Cfg()); m.load_state_dict(sd); m = m.cuda().train()
 for _ in range(3):
-    m.zero_grad(); m.addGSO(St); loss = po.planner_loss(m(xt), tt); loss.backward()
+    m.zero_grad(); m.addGSO(St); loss = gp.planner_loss(m.forward_logits(xt), tt); loss.backward()
 torch.cuda.synchronize()

@@ -1,5 +1,5 @@
-"""One training step (forward + loss + backward + Adam) at BASELINE configs 3 and 5 (per-GPU shard), native kernels vs
-the batched-torch path, device-resident, CUDA events; CPU oracle step timed beside it (bounded).
+"""One training step (forward + fused loss + backward + Adam) at BASELINE configs 3 and 5 (per-GPU shard), device-resident,
+CUDA events; CPU oracle step timed beside it (bounded).
 usage: python profiles/train_microbench.py"""
 import os
 import sys
@@ -23,19 +23,14 @@ for (N, K, B, W, name) in [(10, 3, 64, 20, "C3 (K3,N10,B64)"), (20, 3, 64, 28, "
     x, S = synthetic.make_batch(B, N, W, seed=3)
     tgt = torch.from_numpy(synthetic.random_targets(B, N, seed=4))
     xt, St, tt = torch.from_numpy(x).cuda(), torch.from_numpy(S).cuda(), tgt.cuda()
-    for path in ("native", "torch"):
+    for path in ("native",):
         m = gp.DecentralPlannerNet(Cfg(N, K)); m.load_state_dict(sd); m = m.cuda().train()
         opt = torch.optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
 
         def step():
             opt.zero_grad(set_to_none=True)
             m.addGSO(St)
-            if path == "native":
-                out = m(xt)
-            else:
-                m.GFL[0].addGSO(m.S)
-                out = list(m._forward_autograd(xt, m.S).unbind(0))
-            loss = po.planner_loss(out, tt)
+            loss = gp.planner_loss(m.forward_logits(xt), tt)
             loss.backward()
             opt.step()
         for _ in range(5):
