@@ -738,11 +738,88 @@ static inline int grid_for(long long total, int block = 256) {
 }
 
 // the planner's maps are 11x11, 5x5 and 2x2: row-tiled kernels; anything else: the generic kernels
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 convolution (pad 1) on 2x2 maps as a shared-memory-tiled GEMM, forward and input-gradient in one template:
+//   O[img][n][p] = bias[n] + sum_k sum_q I[img][k][q] * w(n, k, tap(p, q))        p, q = the 4 pixels of the map
+// FWD: n = output channel, k = input channel, tap = (qy - py + 1, qx - px + 1), w = W[n][k];
+// BWD: n = input channel,  k = output channel, tap = (py - qy + 1, px - qx + 1), w = W[k][n]  (din from dz).
+// Block = 16 images x 32 n (256 threads: one image x 4 n x 4 pixels per thread), K staged 8 at a time: inputs [16][8][4],
+// weights [8][9][32] read from the raw [Cout][Cin][3][3] layout in contiguous runs.  The thread-per-(4 images, channel)
+// kernels above read the weights with a 2.3 KB stride between lanes and launched 40-80 blocks: 96 / 73 us per call at
+// 640 images; these take a few us.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(256) conv2x2_gemm_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int M,
+                                                           int K, int NO, int Cin) {
+    __shared__ __align__(16) float sI[16][8][4];
+    __shared__ __align__(16) float sW[8][9][32];
+    const int tid = threadIdx.x, nq = tid & 7;                         // 8 n-quads = 32 n per block, 16 images,
+    const int half = (tid >> 7) & 1;                                    // and the two pixel pairs {0,1} / {2,3}
+    const int img_l = (tid >> 3) & 15;
+    const int img0 = blockIdx.x * 16, n0 = blockIdx.y * 32;
+    float acc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float bv = (!BWD && bias) ? bias[n0 + 4 * nq + j] : 0.f;
+        acc[j][0] = bv; acc[j][1] = bv;
+    }
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        __syncthreads();
+        if (tid < 128) {                                                // inputs: 16 images x 8 k x float4
+            const int ii = tid >> 3, kk = tid & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (img0 + ii < M) v = *reinterpret_cast<const float4*>(in + ((size_t)(img0 + ii) * K + k0 + kk) * 4);
+            *reinterpret_cast<float4*>(&sI[ii][kk][0]) = v;
+        }
+        for (int e = tid; e < 8 * 9 * 32; e += 256) {                   // weights
+            int kk, t, n;
+            size_t src;
+            if (!BWD) {          // runs of 72 floats: w[n][k0 .. k0+7][0..8]
+                n = e / 72; const int r = e - n * 72; kk = r / 9; t = r - kk * 9;
+                src = ((size_t)(n0 + n) * Cin + k0 + kk) * 9 + t;
+            } else {             // runs of 288 floats: w[k0+kk][n0 .. n0+31][0..8]
+                kk = e / 288; const int r = e - kk * 288; n = r / 9; t = r - n * 9;
+                src = ((size_t)(k0 + kk) * Cin + n0 + n) * 9 + t;
+            }
+            sW[kk][t][n] = w[src];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const float4 iv = *reinterpret_cast<const float4*>(&sI[img_l][kk][0]);
+            const float q[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int p = 2 * half + pp, py = p >> 1, px = p & 1;
+#pragma unroll
+                for (int qi = 0; qi < 4; ++qi) {
+                    const int qy = qi >> 1, qx = qi & 1;
+                    const int t = BWD ? ((py - qy + 1) * 3 + (px - qx + 1)) : ((qy - py + 1) * 3 + (qx - px + 1));
+                    const float4 wv = *reinterpret_cast<const float4*>(&sW[kk][0][0] + ((size_t)t * 32 + 4 * nq));
+                    acc[0][pp] = fmaf(q[qi], wv.x, acc[0][pp]);
+                    acc[1][pp] = fmaf(q[qi], wv.y, acc[1][pp]);
+                    acc[2][pp] = fmaf(q[qi], wv.z, acc[2][pp]);
+                    acc[3][pp] = fmaf(q[qi], wv.w, acc[3][pp]);
+                }
+            }
+        }
+    }
+    if (img0 + img_l < M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float2*>(out + ((size_t)(img0 + img_l) * NO + n0 + 4 * nq + j) * 4 + 2 * half) =
+                make_float2(acc[j][0], acc[j][1]);
+    }
+}
+
 static void launch_conv_fwd(const float* in, const float* w, const float* b, float* out, int M, int Cin, int Cout, int H,
                             cudaStream_t st) {
     const long long rows = (long long)M * Cout * H;
     if (H == 11) conv3x3_fwd_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
     else if (H == 5) conv3x3_fwd_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
+    else if (H == 2 && Cin % 8 == 0 && Cout % 32 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0)
+        conv2x2_gemm_kernel<false><<<dim3((M + 15) / 16, Cout / 32), 256, 0, st>>>(in, w, b, out, M, Cin, Cout, Cin);
     else if (H == 2 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0)
         conv3x3_fwd_2x2_kernel<<<grid_for((long long)((M + 3) / 4) * Cout), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
     else if (H == 2) conv3x3_fwd_rows_kernel<2><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
@@ -753,6 +830,8 @@ static void launch_conv_bwd_input(const float* dz, const float* w, float* din, i
     const long long rows = (long long)M * Cin * H;
     if (H == 11) conv3x3_bwd_input_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
     else if (H == 5) conv3x3_bwd_input_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
+    else if (H == 2 && Cout % 8 == 0 && Cin % 32 == 0 && ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(din)) & 15u) == 0)
+        conv2x2_gemm_kernel<true><<<dim3((M + 15) / 16, Cin / 32), 256, 0, st>>>(dz, w, nullptr, din, M, Cout, Cin, Cin);
     else if (H == 2 && ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(din)) & 15u) == 0)
         conv3x3_bwd_input_2x2_kernel<<<grid_for((long long)((M + 3) / 4) * Cin), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
     else if (H == 2) conv3x3_bwd_input_rows_kernel<2><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
