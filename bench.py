@@ -58,7 +58,7 @@ FE_FLOPS_PER_AGENT_STEP = 2476224 + 32768          # 5 conv layers + compress ML
 #   profiles/r02_ncu_feature_mma_c2.csv: feature_mma_kernel per C2 launch (640 agent-steps); r01_ncu_full_summary_*.csv:
 #   gf_fwd_kernel 0.619 MB per C2 launch
 #   profiles/r02_ncu_pair_v13_summary.txt: gf_fwd_pair_kernel 664.35 MB for 65,536 episodes x 10 agents
-NCU_FE_BYTES_PER_AGENT_STEP = 1.645e6 / 640
+NCU_FE_BYTES_PER_AGENT_STEP = 1.752576e6 / 640        # feature_mma_kernel: 0.93 MB of inputs + 0.63 MB of filter images + constants
 NCU_GF_BYTES_PER_AGENT_STEP = 0.619e6 / 640
 NCU_PAIR_BYTES_PER_AGENT_STEP = 664.35e6 / 655360
 
