@@ -813,10 +813,84 @@ __global__ void __launch_bounds__(256) conv2x2_gemm_kernel(const float* __restri
     }
 }
 
+// The same formulation on 5x5 maps (conv1, conv2): block = IMGS images x 32 n, 40 threads per image = (map row, n-quad), one
+// thread owns a row of 5 pixels x 4 n; K staged 8 at a time as zero-bordered 7 x 8 planes.  61 / 35 us per call before.
+template <bool BWD, int IMGS>
+__global__ void __launch_bounds__(40 * IMGS) conv5x5_gemm_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int M,
+                                                           int K, int NO, int Cin) {
+    __shared__ __align__(16) float sI[IMGS][8][7][8];       // [image][k][padded row][padded col (7 used)]
+    __shared__ __align__(16) float sW[8][9][32];
+    const int tid = threadIdx.x, nq = tid & 7, row = (tid >> 3) % 5, img_l = tid / 40;
+    constexpr int NT = 40 * IMGS;
+    const int img0 = blockIdx.x * IMGS, n0 = blockIdx.y * 32;
+    for (int e = tid; e < IMGS * 8 * 7 * 8; e += NT) (&sI[0][0][0][0])[e] = 0.f;      // borders stay zero
+    float acc[4][5];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float bv = (!BWD && bias) ? bias[n0 + 4 * nq + j] : 0.f;
+#pragma unroll
+        for (int x = 0; x < 5; ++x) acc[j][x] = bv;
+    }
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        __syncthreads();
+        for (int e = tid; e < IMGS * 8 * 25; e += NT) {                   // inputs: 64 planes of 25 contiguous floats
+            const int pl = e / 25, px = e - pl * 25, ii = pl >> 3, kk = pl & 7;
+            float v = 0.f;
+            if (img0 + ii < M) v = in[((size_t)(img0 + ii) * K + k0 + kk) * 25 + px];
+            sI[ii][kk][px / 5 + 1][px % 5 + 1] = v;
+        }
+        for (int e = tid; e < 8 * 9 * 32; e += NT) {                   // weights (taps flipped for the input gradient)
+            int kk, t, n;
+            size_t src;
+            if (!BWD) {
+                n = e / 72; const int r = e - n * 72; kk = r / 9; t = r - kk * 9;
+                src = ((size_t)(n0 + n) * Cin + k0 + kk) * 9 + t;
+                sW[kk][t][n] = w[src];
+            } else {
+                kk = e / 288; const int r = e - kk * 288; n = r / 9; t = r - n * 9;
+                src = ((size_t)(k0 + kk) * Cin + n0 + n) * 9 + t;
+                sW[kk][8 - t][n] = w[src];
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const float4 i0 = *reinterpret_cast<const float4*>(&sI[img_l][kk][row + ky][0]);
+                const float4 i1 = *reinterpret_cast<const float4*>(&sI[img_l][kk][row + ky][4]);
+                const float v[7] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z};
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&sW[kk][ky * 3 + kx][4 * nq]);
+#pragma unroll
+                    for (int x = 0; x < 5; ++x) {
+                        acc[0][x] = fmaf(v[x + kx], wv.x, acc[0][x]);
+                        acc[1][x] = fmaf(v[x + kx], wv.y, acc[1][x]);
+                        acc[2][x] = fmaf(v[x + kx], wv.z, acc[2][x]);
+                        acc[3][x] = fmaf(v[x + kx], wv.w, acc[3][x]);
+                    }
+                }
+            }
+        }
+    }
+    if (img0 + img_l < M) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float* dst = out + ((size_t)(img0 + img_l) * NO + n0 + 4 * nq + j) * 25 + row * 5;
+#pragma unroll
+            for (int x = 0; x < 5; ++x) dst[x] = acc[j][x];
+        }
+    }
+}
+
 static void launch_conv_fwd(const float* in, const float* w, const float* b, float* out, int M, int Cin, int Cout, int H,
                             cudaStream_t st) {
     const long long rows = (long long)M * Cout * H;
     if (H == 11) conv3x3_fwd_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
+    else if (H == 5 && Cin % 8 == 0 && Cout % 32 == 0)
+        conv5x5_gemm_kernel<false, 4><<<dim3((M + 3) / 4, Cout / 32), 160, 0, st>>>(in, w, b, out, M, Cin, Cout, Cin);
     else if (H == 5) conv3x3_fwd_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(in, w, b, out, M, Cin, Cout);
     else if (H == 2 && Cin % 8 == 0 && Cout % 32 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0)
         conv2x2_gemm_kernel<false><<<dim3((M + 15) / 16, Cout / 32), 256, 0, st>>>(in, w, b, out, M, Cin, Cout, Cin);
@@ -829,6 +903,8 @@ static void launch_conv_bwd_input(const float* dz, const float* w, float* din, i
                                   cudaStream_t st) {
     const long long rows = (long long)M * Cin * H;
     if (H == 11) conv3x3_bwd_input_rows_kernel<11><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
+    else if (H == 5 && Cout % 8 == 0 && Cin % 32 == 0)
+        conv5x5_gemm_kernel<true, 4><<<dim3((M + 3) / 4, Cin / 32), 160, 0, st>>>(dz, w, nullptr, din, M, Cout, Cin, Cin);
     else if (H == 5) conv3x3_bwd_input_rows_kernel<5><<<grid_for(rows), 256, 0, st>>>(dz, w, din, M, Cin, Cout);
     else if (H == 2 && Cout % 8 == 0 && Cin % 32 == 0 && ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(din)) & 15u) == 0)
         conv2x2_gemm_kernel<true><<<dim3((M + 15) / 16, Cin / 32), 256, 0, st>>>(dz, w, nullptr, din, M, Cout, Cin, Cin);
