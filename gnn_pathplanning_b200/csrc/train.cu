@@ -76,8 +76,13 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b) {
 }
 
 // per (agent n, channel c): mean and biased variance over (b, y, x) of z[(b*N+n)][c][:]; one CTA per group
+// Per-agent BatchNorm of one (agent, channel) group per block, fused: batch statistics (two passes, double accumulation) ->
+// a = relu(gamma * (z - mean) * invstd + beta) for the group's own elements -> optional 2x2 max-pool of them.  (The
+// statistics alone used to be one launch, apply and pool two more.)
 __global__ void bn_stats_kernel(const float* __restrict__ z, float* __restrict__ mean, float* __restrict__ var,
-                                float* __restrict__ invstd, int B, int N, int C, int HW, float eps) {
+                                float* __restrict__ invstd, int B, int N, int C, int HW, float eps,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ a,
+                                float* __restrict__ pooled, int H, int Hp) {
     const int n = blockIdx.x / C, c = blockIdx.x - n * C;
     const int cnt = B * HW;
     double s = 0.0, q = 0.0;
@@ -94,11 +99,29 @@ __global__ void bn_stats_kernel(const float* __restrict__ z, float* __restrict__
         d2 += d * d;
     }
     block_reduce2(d2, zero);
+    const float v = (float)(d2 / cnt);
+    const float muf = (float)mu, is = 1.0f / sqrtf(v + eps);
     if (threadIdx.x == 0) {
-        const float v = (float)(d2 / cnt);
-        mean[blockIdx.x] = (float)mu;
+        mean[blockIdx.x] = muf;
         var[blockIdx.x] = v;
-        invstd[blockIdx.x] = 1.0f / sqrtf(v + eps);
+        invstd[blockIdx.x] = is;
+    }
+    if (!a) return;
+    const float ga = gamma[c], be = beta[c];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b = i / HW, p = i - b * HW;
+        const size_t idx = ((size_t)(b * N + n) * C + c) * HW + p;
+        a[idx] = fmaxf(fmaf((z[idx] - muf) * is, ga, be), 0.f);
+    }
+    if (pooled) {
+        const int HWp = Hp * Hp;
+        for (int i = threadIdx.x; i < B * HWp; i += blockDim.x) {
+            const int b = i / HWp, pp = i - b * HWp, py = pp / Hp, px = pp - py * Hp;
+            const float* zp = z + ((size_t)(b * N + n) * C + c) * HW + (2 * py) * H + 2 * px;
+            const float v0 = fmaxf(fmaf((zp[0] - muf) * is, ga, be), 0.f), v1 = fmaxf(fmaf((zp[1] - muf) * is, ga, be), 0.f);
+            const float v2 = fmaxf(fmaf((zp[H] - muf) * is, ga, be), 0.f), v3 = fmaxf(fmaf((zp[H + 1] - muf) * is, ga, be), 0.f);
+            pooled[((size_t)(b * N + n) * C + c) * HWp + pp] = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        }
     }
 }
 
@@ -309,10 +332,13 @@ __global__ void maxpool2_bwd_kernel(const float* __restrict__ a, const float* __
 }
 
 // per (n,c): s1 = sum dy_eff, s2 = sum dy_eff * xhat, dy_eff = da * (a > 0), xhat = (z - mean) * invstd
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ a,
+// One (agent, channel) group per block: s1 = sum dy, s2 = sum dy * xhat (double), then -- the block owns every element of
+// the group -- dz = gamma * invstd * (dy - s1/m - xhat * s2/m) in place over da (evaluated in double like the reference's
+// CPU kernel: for groups with near-zero variance invstd is ~316 and dy - mean(dy) cancels almost exactly).
+__global__ void bn_bwd_reduce_kernel(float* __restrict__ da, const float* __restrict__ a,
                                      const float* __restrict__ z, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, double* __restrict__ s1, double* __restrict__ s2,
-                                     int B, int N, int C, int HW) {
+                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                     double* __restrict__ s1, double* __restrict__ s2, int B, int N, int C, int HW) {
     const int n = blockIdx.x / C, c = blockIdx.x - n * C;
     const int cnt = B * HW;
     const float mu = mean[blockIdx.x], is = invstd[blockIdx.x];
@@ -328,6 +354,14 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ da, const float* 
     if (threadIdx.x == 0) {
         s1[blockIdx.x] = t1;
         s2[blockIdx.x] = t2;
+    }
+    const double inv_m = 1.0 / (double)cnt, isd = (double)is, gad = (double)gamma[c];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int b = i / HW, p = i - b * HW;
+        const size_t idx = ((size_t)(b * N + n) * C + c) * HW + p;
+        const double dy = a[idx] > 0.f ? (double)da[idx] : 0.0;
+        const double xhat = ((double)z[idx] - (double)mu) * isd;
+        da[idx] = (float)(gad * isd * (dy - t1 * inv_m - xhat * t2 * inv_m));
     }
 }
 // dgamma[c] = sum_n s2[n][c], dbeta[c] = sum_n s1[n][c]
@@ -951,25 +985,18 @@ extern "C" int gpp_planner_train_forward(const gpp_planner_weights* w, const gpp
         float* a = ws + L.a[l];
         launch_conv_fwd(in, w->conv_w[l], w->conv_b[l], z, M, Cin, Cout, H, st);
         GPP_LAUNCH_CHECK();
-        bn_stats_kernel<<<N * Cout, 128, 0, st>>>(z, ws + L.mean[l], ws + L.var[l], ws + L.invstd[l], B, N, Cout, HW, 1e-5f);
+        const bool pool = pooled_after(l);
+        bn_stats_kernel<<<N * Cout, 128, 0, st>>>(z, ws + L.mean[l], ws + L.var[l], ws + L.invstd[l], B, N, Cout, HW, 1e-5f,
+                                                  w->bn_w[l], w->bn_b[l], a, pool ? ws + L.p[l] : nullptr, H,
+                                                  pool ? pooled_hw(l) : 0);
         GPP_LAUNCH_CHECK();
-        bn_apply_relu_kernel<<<grid_for(total), 256, 0, st>>>(z, ws + L.mean[l], ws + L.invstd[l], w->bn_w[l], w->bn_b[l],
-                                                              a, total, N, Cout, HW);
-        GPP_LAUNCH_CHECK();
+        (void)total;
         if (bn && bn->running_mean[l] && bn->running_var[l]) {
             bn_running_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(ws + L.mean[l], ws + L.var[l], bn->running_mean[l],
                                                                   bn->running_var[l], N, Cout, B * HW, momentum);
             GPP_LAUNCH_CHECK();
         }
-        if (pooled_after(l)) {
-            const int Hp = pooled_hw(l);
-            const long long tp = (long long)M * Cout * Hp * Hp;
-            maxpool2_fwd_kernel<<<grid_for(tp), 256, 0, st>>>(a, ws + L.p[l], tp, H, Hp);
-            GPP_LAUNCH_CHECK();
-            in = ws + L.p[l];
-        } else {
-            in = a;
-        }
+        in = pool ? ws + L.p[l] : a;
     }
     linear128_fwd_rowwarp_kernel<<<(M + 7) / 8, 256, 0, st>>>(in, w->compress_w, w->compress_b, ws + L.feat, M, 1);
     GPP_LAUNCH_CHECK();
@@ -1040,12 +1067,10 @@ extern "C" int gpp_planner_train_backward(const gpp_planner_weights* w, const fl
         }
         double* s1 = reinterpret_cast<double*>(ws + L.s1);
         double* s2 = reinterpret_cast<double*>(ws + L.s2);
-        bn_bwd_reduce_kernel<<<N * Cout, 128, 0, st>>>(da, a, z, ws + L.mean[l], ws + L.invstd[l], s1, s2, B, N, Cout, HW);
+        bn_bwd_reduce_kernel<<<N * Cout, 128, 0, st>>>(da, a, z, ws + L.mean[l], ws + L.invstd[l], w->bn_w[l], s1, s2, B, N,
+                                                       Cout, HW);
         GPP_LAUNCH_CHECK();
         bn_param_grad_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(s1, s2, g->bn_w[l], g->bn_b[l], N, Cout);
-        GPP_LAUNCH_CHECK();
-        bn_bwd_apply_kernel<<<grid_for(total), 256, 0, st>>>(da, a, z, ws + L.mean[l], ws + L.invstd[l], w->bn_w[l],
-                                                             s1, s2, total, B, N, Cout, HW);
         GPP_LAUNCH_CHECK();
         // da now holds dz
         const float* lin = (l == 0) ? x : (pooled_after(l - 1) ? ws + L.p[l - 1] : ws + L.a[l - 1]);
