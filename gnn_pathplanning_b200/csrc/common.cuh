@@ -133,4 +133,36 @@ __device__ __forceinline__ float4 ld_smem4(const float* p) {
     return *reinterpret_cast<const float4*>(p);
 }
 
+// ---- packed fp32 arithmetic (sm_100: SASS FFMA2 / FMUL2 / FADD2).  One instruction = one issue slot for two IEEE fp32
+//      operations with the rounding of the scalar forms, so results are bit-identical; a scalar factor is broadcast by
+//      the instruction itself (operand modifier .F32), no extra move.  The fp32 pipe's rate is unchanged (128 FMA / clk /
+//      SM, profiles/probes/ffma2_probe.cu): this halves ISSUE pressure where FMAs compete with loads, conversions and
+//      stores for the scheduler. ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// (c0, c1) = s * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void ffma2_s(float s, float b0, float b1, float& c0, float& c1) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(s, s)), "l"(f2_pack(b0, b1)), "l"(f2_pack(c0, c1)));
+    f2_unpack(d, c0, c1);
+}
+// (c0, c1) = s * (b0, b1)
+__device__ __forceinline__ void fmul2_s(float s, float b0, float b1, float& c0, float& c1) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(s, s)), "l"(f2_pack(b0, b1)));
+    f2_unpack(d, c0, c1);
+}
+// (c0, c1) = (a0, a1) - (b0, b1)
+__device__ __forceinline__ void fsub2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a0, a1)), "l"(f2_pack(b0, b1)));
+    f2_unpack(d, c0, c1);
+}
+
 }  // namespace gpp

@@ -154,7 +154,10 @@ __device__ __forceinline__ void gp_arrive(uint64_t* bar) {
 __device__ __forceinline__ void gp_split4(const float4 v, uint2& hi, uint2& lo) {
     const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
     const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    float r0, r1, r2, r3;
+    fsub2(v.x, v.y, f01.x, f01.y, r0, r1);
+    fsub2(v.z, v.w, f23.x, f23.y, r2, r3);
+    const __half2 l01 = __floats2half2_rn(r0, r1), l23 = __floats2half2_rn(r2, r3);
     hi.x = *reinterpret_cast<const uint32_t*>(&h01);
     hi.y = *reinterpret_cast<const uint32_t*>(&h23);
     lo.x = *reinterpret_cast<const uint32_t*>(&l01);
@@ -182,15 +185,11 @@ __device__ __forceinline__ void gp_propagate_half(const float* __restrict__ Ms, 
 #pragma unroll
         for (int i = 0; i < CNT; ++i) {
             if (m == 0) {        // first term: no accumulator to clear
-                out[i].x = sv[i] * in[m].x;
-                out[i].y = sv[i] * in[m].y;
-                out[i].z = sv[i] * in[m].z;
-                out[i].w = sv[i] * in[m].w;
-            } else {
-                out[i].x = fmaf(sv[i], in[m].x, out[i].x);
-                out[i].y = fmaf(sv[i], in[m].y, out[i].y);
-                out[i].z = fmaf(sv[i], in[m].z, out[i].z);
-                out[i].w = fmaf(sv[i], in[m].w, out[i].w);
+                fmul2_s(sv[i], in[m].x, in[m].y, out[i].x, out[i].y);
+                fmul2_s(sv[i], in[m].z, in[m].w, out[i].z, out[i].w);
+            } else {             // packed FFMA2: half the issue slots of four scalar FMAs, same rounding
+                ffma2_s(sv[i], in[m].x, in[m].y, out[i].x, out[i].y);
+                ffma2_s(sv[i], in[m].z, in[m].w, out[i].z, out[i].w);
             }
         }
     }
@@ -202,6 +201,14 @@ __device__ __forceinline__ void gp_row_addrs(uint32_t unit0, int row0, int l8, u
 }
 __device__ __forceinline__ void gp_sts64(uint32_t addr, uint2 v) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void gp_store_row(const uint32_t (&ahi)[N], int n, uint32_t tap_off, const float4 v) {
+    uint2 hi, lo;
+    gp_split4(v, hi, lo);
+    const uint32_t addr = ahi[n] + tap_off;
+    gp_sts64(addr, hi);
+    gp_sts64(addr ^ 64u, lo);             // units are 1024-byte aligned: the xor never carries
 }
 // rows N0 .. N0+CNT-1 of the item's sample: split and store this lane's 4 features
 template <int N, int N0, int CNT>
@@ -343,6 +350,9 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         // path of the whole kernel (33 K cycles per tile, profiles/r02_pair_phase_v1.txt); their loads hit L2 thanks to
         // the bulk prefetch issued two tiles earlier.
         const int sw = warp - GP_SCOUT_WARP0;
+        for (int i = sw * 32 + lane; i < 2 * (int)(L.s_bytes / 4); i += GP_SCOUT_WARPS * 32)
+            reinterpret_cast<float*>(sm + L.s_off)[i] = 0.f;        // pad slots of the staged rows: never written again
+        asm volatile("bar.sync 1, %0;" ::"r"(GP_SCOUT_WARPS * 32) : "memory");
         int t = 0;
         for (int p = cluster_id; p < a.num_pairs; p += num_clusters, ++t) {
             const int tile = 2 * p + (int)rank;
@@ -420,11 +430,9 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
 #pragma unroll
                         for (int m = 0; m < N; ++m) cs += fabsf(Sd[(sl * N + m) * NP + gp_slot(N, lane)]);
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                        cs = fmaxf(cs, __shfl_xor_sync(0xffffffffu, cs, o));
-                    }
+                    // both are >= 0: the order of the bit patterns is the order of the values (one REDUX each)
+                    mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(mx)));
+                    cs = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(cs)));
                     float bound = mx;
                     const float cm = fmaxf(cs, 1.f);
                     for (int k = 1; k < K; ++k) bound *= cm;
@@ -444,18 +452,25 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 }
                 if (K > 2 && v) {
                     // S.S for the third tap: z_2 = (x.S).S = x.(S.S), so the producers form every tap straight from x
+                    // lane = (row m, 4-slot part of the staged row): 1 scalar + 1 vector load and 2 FFMA2 per term
                     float* S2d = Sd + TS * N * NP;
+                    constexpr int PARTS = NP / 4;
+                    static_assert(N * PARTS <= 32, "one lane per (row, 4-slot part)");
+                    if (lane < N * PARTS) {
+                        const int m = lane / PARTS, part = lane - m * PARTS;
+                        const float* rowm = Sd + (sl * N + m) * NP;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int e = 4 * lane + i;
-                        if (e < N * N) {
-                            const int m = e / N, n = e % N;
-                            float acc = 0.f;
-#pragma unroll
-                            for (int jj = 0; jj < N; ++jj)
-                                acc = fmaf(Sd[(sl * N + m) * NP + gp_slot(N, jj)], Sd[(sl * N + jj) * NP + gp_slot(N, n)], acc);
-                            S2d[(sl * N + m) * NP + gp_slot(N, n)] = acc * e2;      // carries the sample's scale: tap-2 items use x as it is
+                        for (int jj = 0; jj < N; ++jj) {
+                            const float sj = rowm[gp_slot(N, jj)];
+                            const float4 r4 = ld_smem4(Sd + (sl * N + jj) * NP + 4 * part);
+                            ffma2_s(sj, r4.x, r4.y, acc.x, acc.y);
+                            ffma2_s(sj, r4.z, r4.w, acc.z, acc.w);
                         }
+                        // carries the sample's scale: tap-2 items use x as it is (unused pad slots stay finite: S pads are zero)
+                        fmul2_s(e2, acc.x, acc.y, acc.x, acc.y);
+                        fmul2_s(e2, acc.z, acc.w, acc.z, acc.w);
+                        *reinterpret_cast<float4*>(S2d + (sl * N + m) * NP + 4 * part) = acc;
                     }
                 }
             }
@@ -586,7 +601,7 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         const int total_items = ntile_seq * ipt;
         uint32_t ahi0[N];                              // operand row addresses of tap 0 (same rows, same slot every item)
         gp_row_addrs<N>(smem_u32(sm + L.a_off + (size_t)slot * K * L.a_unit), sl * N, l8, ahi0);
-        const bool has_work = kind == 0 || K > 2;      // (K < 3: the kind-1 warps only keep the barrier counts)
+        const bool has_work = kind == 0 || K > 2;      // (K < 3: the kind-1 warps only store their half of tap 0)
         const bool st_ok = !(a.ablate & 2);
         int cur_tile = -1;
         for (int I = warp; I < total_items; I += GP_PROD_WARPS) {
@@ -595,7 +610,7 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
             const uint32_t g = (uint32_t)(tt * GP_NCHUNK + c);
             const int sb = tt & 1;
             const int smp = (2 * (cluster_id + tt * num_clusters) + (int)rank) * TS + sl;
-            const bool sv = smp < a.B && has_work && !(a.ablate & 4);
+            const bool sv = smp < a.B && !(a.ablate & 4);
             float4 xv[N];
             const float* xp = a.x + ((size_t)smp * N) * GP_C + c * 32 + l8 * 4;
 #pragma unroll
@@ -611,11 +626,16 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 GP_ACC(0);
                 cur_tile = tt;
             }
-            if (kind == 0) {        // (the staged S.S already carries the scale)
-                const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
+            // Tap 0 (the scaled x itself) is split between the two kinds -- kind 0: rows [0, H0) + tap 1, kind 1: rows
+            // [H0, N) + tap 2 -- so that both warps of an item carry the same number of instructions (an item's LATENCY is
+            // what the ring waits for).  Tap 1 needs the scaled x; the staged S.S already carries the scale.
+            constexpr int H0 = N / 2;
+            const float scale = sv ? scale_p[sb * GP_MAX_TS + sl] : 1.f;
+            if (kind == 0) {
 #pragma unroll
                 for (int n = 0; n < N; ++n) {
-                    xv[n].x *= scale; xv[n].y *= scale; xv[n].z *= scale; xv[n].w *= scale;
+                    fmul2_s(scale, xv[n].x, xv[n].y, xv[n].x, xv[n].y);
+                    fmul2_s(scale, xv[n].z, xv[n].w, xv[n].z, xv[n].w);
                 }
             }
             const float* Ms = reinterpret_cast<const float*>(sm + L.s_off + sb * L.s_bytes) + (size_t)sl * N * NP;
@@ -625,8 +645,18 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
                 GP_ACC(1);
             }
             if (kind == 0) {
-                if (st_ok) gp_store_rows<N, 0, N>(ahi0, 0u, xv);
+#pragma unroll
+                for (int n = 0; n < H0; ++n) {
+                    if (st_ok) gp_store_row<N>(ahi0, n, 0u, xv[n]);
+                }
             } else {
+#pragma unroll
+                for (int n = H0; n < N; ++n) {
+                    float4 t;
+                    fmul2_s(scale, xv[n].x, xv[n].y, t.x, t.y);
+                    fmul2_s(scale, xv[n].z, xv[n].w, t.z, t.w);
+                    if (st_ok) gp_store_row<N>(ahi0, n, 0u, t);
+                }
                 Ms += (size_t)TS * N * NP;          // S.S follows S in the buffer
             }
             if (has_work && (kind == 1 || K > 1) && !(a.ablate & 1)) {

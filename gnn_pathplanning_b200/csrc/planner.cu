@@ -100,6 +100,13 @@ size_t feature_tc_image_floats(int L);
 int launch_prep_feature_tc(const float* w, float* img, int L, cudaStream_t st);
 int launch_feature_tc_kernel(const FeArgs& fa, const float* const* imgs, cudaStream_t st);
 int debug_feature_tc_timing(unsigned long long* out20);
+// small-batch tcgen05 graph filter + action MLP (graph_filter_small.cu)
+size_t gf_small_arena_bytes(int K);
+bool gf_small_supported(int N, int K);
+int launch_prep_gf_small(const float* w, float* arena, int K, cudaStream_t st);
+int launch_gf_forward_small(const float* x, const void* S, int s_is_f64, const float* arena, const float* bias,
+                            const float* wa, const float* ba, float* logits, int B, int K, float* lpart,
+                            unsigned int* tickets, int pdl, cudaStream_t st);
 // im2col-free fp16-split tensor-core feature extractor (feature_mma.cu)
 size_t feature_mma_arena_floats();
 int launch_prep_feature_mma(const float* const* conv_w, const float* compress_w, const float* const* sc,
@@ -143,6 +150,7 @@ struct gpp_planner {
     int gf_mode;         // 0 auto, 1 CUDA-core kernel, 2 tcgen05 3xTF32 kernel, 3 tcgen05 CTA-pair fp16-split kernel
     int fe_mode;         // feature extractor: 0 auto, 1 CUDA-core kernel, 2 tcgen05 3xTF32 kernel, 3 tcgen05 fp16-split kernel
     size_t off_fmma;     // images + constants of the fp16-split kernel
+    size_t off_gfsmall;  // tap images of the small-batch tcgen05 graph filter
     size_t off_fimg[6];  // tcgen05 filter chunk images of conv0..4 and the compress MLP
     bool weights_set;
     float* raw;          // device staging for host-provided parameters
@@ -226,6 +234,7 @@ extern "C" int gpp_planner_create(gpp_planner** out, int K) {
     p->off_gfpair = take(K <= 3 ? gf_pair_image_bytes(K) / 4 + 16 : 16);
     for (int l = 0; l < 6; ++l) p->off_fimg[l] = take(feature_tc_image_floats(l));
     p->off_fmma = take(feature_mma_arena_floats());
+    p->off_gfsmall = take(K <= 3 ? gf_small_arena_bytes(K) / 4 + 16 : 16);
     p->arena_floats = off;
     if (cudaMalloc(&p->arena, sizeof(float) * off) != cudaSuccess) {
         set_error("planner_create: cudaMalloc(%zu) failed", sizeof(float) * off);
@@ -444,6 +453,8 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     if (K <= 3) {
         rc = launch_prep_pair_taps(d.gf_w, A + p->off_gfpair, K, st);
         if (rc) return rc;
+        rc = launch_prep_gf_small(d.gf_w, A + p->off_gfsmall, K, st);
+        if (rc) return rc;
     }
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_b5, d.compress_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
     GPP_CUDA_OK(cudaMemcpyAsync(A + p->off_gfb, d.gf_b, sizeof(float) * 128, cudaMemcpyDeviceToDevice, st));
@@ -560,7 +571,15 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
                 "planner_forward: CTA-pair graph filter requested but N=%d K=%d is outside its envelope", N, p->K);
     const bool use_pair = pair_fits && (p->gf_mode == 3 || (p->gf_mode == 0 && rows >= 4096));
     const bool use_tc = !use_pair && tc_fits && (p->gf_mode == 2 || (p->gf_mode == 0 && rows >= 4096));
-    if (use_pair)
+    // small batches at N = 10 (the benchmark configuration, rollout steps): 2 CTAs per 6 samples on the tensor core
+    const bool use_small = !use_pair && p->gf_mode == 0 && gf_small_supported(N, p->K) && !debug_option(DBG_GF_MODE);
+    if (use_small) {
+        rc = ensure_gf_scratch(p, rows, st);
+        if (rc) return rc;
+        rc = launch_gf_forward_small(feat, S, s_is_f64, A + p->off_gfsmall, A + p->off_gfb, A + p->off_wa, A + p->off_ba,
+                                     logits, B, p->K, p->gf_lpart,
+                                     reinterpret_cast<unsigned int*>(p->gf_lpart + 10 * p->gf_lpart_rows), pdl, st);
+    } else if (use_pair)
         rc = launch_gf_forward_pair(feat, S, s_is_f64, A + p->off_gfpair, A + p->off_gfb, nullptr, p->wa_host,
                                     p->wa_host + 640, logits, B, N, p->K, 1, st);
     else if (use_tc)
