@@ -586,12 +586,17 @@ gf_fwd_pair_kernel(const __grid_constant__ GpArgs a) {
         constexpr int ipt = ipg * GP_NCHUNK;           // items per tile
         static_assert(2 * ipg == GP_PROD_WARPS, "producer warps = the items of the two ring groups");
         static_assert((TS % 4) == 0, "item = 4 whole samples");
-        // An item = (tile, 32-feature chunk, quad of 4 samples, kind): kind 0 stores tap 0 (x) and tap 1 (x.S), kind 1
-        // stores tap 2 (x.(S.S)) -- every tap comes straight from x, so the two kinds are independent and run on two
-        // warps (what bounds the ring is the LATENCY of an item: a slot is busy from the first operand store until the
+        // An item = (tile, 32-feature chunk, quad of 4 samples, kind): kind 0 stores the first half of the rows of tap 0
+        // (x) and tap 1 (x.S), kind 1 the other rows of tap 0 and tap 2 (x.(S.S)) -- every tap comes straight from x, so the
+        // two kinds are independent and run on two warps (what bounds the ring is the LATENCY of an item: a slot is busy from the first operand store until the
         // MMAs that read it have completed).  Warp w always works on ring slot w / 6, quad (w % 6) % 3, kind (w % 6) / 3;
         // its items are I = w, w + 12, ... of the CTA's sequence (tile I / 24, chunk (I % 24) / 6).
-        const int ql = lane >> 3;
+        // lanes 0-7 | 8-15 | 16-23 | 24-31 work for samples 0 | 2 | 1 | 3 of the quad: a 64-bit shared store is served one
+        // half-warp at a time, and rows 2 samples (20 rows) apart differ in bit 2 of (row & 7), i.e. land in opposite
+        // 64-byte halves of the 128-byte swizzled row -- every operand store is then conflict-free (with samples 0, 1 in
+        // one half-warp half of the row positions collided: 31 % of the kernel's shared-memory wavefronts were conflicts,
+        // profiles/r02_ncu_pair_v13_summary.txt)
+        const int ql = ((lane >> 3) & 1) * 2 + (lane >> 4);
         const int l8 = lane & 7;
         const int slot = warp / ipg;
         const int kind = (warp % ipg) / nquad;

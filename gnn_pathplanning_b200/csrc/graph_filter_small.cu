@@ -47,6 +47,7 @@ struct GsMisc {
     uint64_t w_full, mma_done;
     uint32_t tmem_slot, is_last;
     uint32_t xmax[GS_TS];
+    uint32_t colmax[GS_TS];
     float inv[GS_TS];
 };
 
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArg
         for (int k = 0; k < K; ++k)
             bulk_g2s(sm + L.w_off + k * 16 * GS_W_PLANE, src + (size_t)k * 16 * GS_W_PLANE, 16 * GS_W_PLANE, &ms->w_full);
     }
-    if (tid < GS_TS) ms->xmax[tid] = 0;
+    if (tid < GS_TS) { ms->xmax[tid] = 0; ms->colmax[tid] = 0; }
     if (warp == 0) tmem_alloc<GS_TMEM_COLS>(&ms->tmem_slot);
     for (int i = tid; i < 5 * 64; i += GS_THREADS) was[i] = __ldg(a.wa + (i >> 6) * 128 + half * 64 + (i & 63));
     if (tid < 64) biass[tid] = __ldg(a.bias + half * 64 + tid);
@@ -151,33 +152,48 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArg
             }
             Ss[tid] = v;
         }
+        if (K >= 2 && tid < GS_TS * GS_N) {       // largest absolute column sum of each sample's S (thread = one column)
+            const int sb = tid / GS_N, n = tid - sb * GS_N;
+            if (sb < ns) {
+                const size_t idx = (size_t)(b0 + sb) * GS_N * GS_N + n;
+                float cs = 0.f;
+#pragma unroll
+                for (int m = 0; m < GS_N; ++m)
+                    cs += fabsf(a.s_is_f64 ? (float)reinterpret_cast<const double*>(a.S)[idx + m * GS_N]
+                                           : reinterpret_cast<const float*>(a.S)[idx + m * GS_N]);
+                atomicMax(&ms->colmax[sb], __float_as_uint(cs));
+            }
+        }
     }
     __syncthreads();
     {
+        // z_1 = x S, z_2 = z_1 S for this thread's feature: two output nodes per packed FFMA2 (rows of S are read as
+        // 8-byte pairs, the node value is the broadcast scalar)
         float z1[GS_N], z2[GS_N];
-        float colmax = 0.f;
+        const float colmax = __uint_as_float(ms->colmax[s]);
         const float* Sp = Ss + s * GS_N * GS_N;
         if (K >= 2) {
 #pragma unroll
-            for (int n = 0; n < GS_N; ++n) {
-                float acc = 0.f, cs = 0.f;
+            for (int n = 0; n < GS_N; ++n) z1[n] = 0.f;
 #pragma unroll
-                for (int m = 0; m < GS_N; ++m) {
-                    const float sv = Sp[m * GS_N + n];
-                    acc = fmaf(xv[m], sv, acc);
-                    cs += fabsf(sv);
+            for (int m = 0; m < GS_N; ++m) {
+#pragma unroll
+                for (int n = 0; n < GS_N; n += 2) {
+                    const float2 sv = *reinterpret_cast<const float2*>(Sp + m * GS_N + n);
+                    ffma2_s(xv[m], sv.x, sv.y, z1[n], z1[n + 1]);
                 }
-                z1[n] = acc;
-                colmax = fmaxf(colmax, cs);
             }
         }
         if (K >= 3) {
 #pragma unroll
-            for (int n = 0; n < GS_N; ++n) {
-                float acc = 0.f;
+            for (int n = 0; n < GS_N; ++n) z2[n] = 0.f;
 #pragma unroll
-                for (int m = 0; m < GS_N; ++m) acc = fmaf(z1[m], Sp[m * GS_N + n], acc);
-                z2[n] = acc;
+            for (int m = 0; m < GS_N; ++m) {
+#pragma unroll
+                for (int n = 0; n < GS_N; n += 2) {
+                    const float2 sv = *reinterpret_cast<const float2*>(Sp + m * GS_N + n);
+                    ffma2_s(z1[m], sv.x, sv.y, z2[n], z2[n + 1]);
+                }
             }
         }
         // |z_k| <= max|x| * max(1, colsum)^k: one power of two per sample
@@ -227,9 +243,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArg
         tcgen05_fence_after();
         const int row = q * 16 + (lane & 15);
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + hsel * 32;
-        float ah[32], al[32];
-        {
-            uint32_t r[32];
+        const int srow = row / GS_N;
+        const float inv = ms->inv[srow < GS_TS ? srow : 0];
+        float p[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #define GS_LD16(dst, col)                                                                                              \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
@@ -238,29 +254,21 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArg
                    "=r"(dst[14]), "=r"(dst[15])                                                                        \
                  : "r"(taddr + (col))                                                                                  \
                  : "memory")
-            uint32_t* r0 = r;
-            uint32_t* r1 = r + 16;
-            GS_LD16(r0, 0);
-            GS_LD16(r1, 16);
+#pragma unroll
+        for (int h16 = 0; h16 < 2; ++h16) {      // 16 columns at a time: A_hi x W_hi + A_lo x W_hi | A_hi x W_lo
+            uint32_t rh[16], rl[16];
+            GS_LD16(rh, h16 * 16);
+            GS_LD16(rl, 64 + h16 * 16);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ah[i] = __uint_as_float(r[i]);
-            GS_LD16(r0, 64);
-            GS_LD16(r1, 80);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int c = 0; c < 16; ++c) {
+                const int col = hsel * 32 + h16 * 16 + c;
+                const float y = fmaxf(fmaf(__uint_as_float(rh[c]) + __uint_as_float(rl[c]), inv, biass[col]), 0.f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) al[i] = __uint_as_float(r[i]);
+                for (int q5 = 0; q5 < 5; ++q5) p[q5] = fmaf(y, was[q5 * 64 + col], p[q5]);
+            }
+        }
 #undef GS_LD16
-        }
-        const int srow = row / GS_N;
-        const float inv = ms->inv[srow < GS_TS ? srow : 0];
-        float p[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float y = fmaxf(fmaf(ah[c] + al[c], inv, biass[hsel * 32 + c]), 0.f);
-#pragma unroll
-            for (int q5 = 0; q5 < 5; ++q5) p[q5] = fmaf(y, was[q5 * 64 + hsel * 32 + c], p[q5]);
-        }
         if (lane < 16 && row < nrows) {
 #pragma unroll
             for (int q5 = 0; q5 < 5; ++q5) part[(hsel * 64 + row) * 8 + q5] = p[q5];
