@@ -5,8 +5,9 @@
 //   y = ReLU(sum_k (x S^k) W_k + b),  logits = y Wa^T + ba          (/root/reference/utils/graphUtils/graphML.py:2342-2366,
 //                                                                    graphs/models/decentralplanner.py:221,301-318)
 //
-// One CTA = 6 samples (60 node rows, one M = 64 accumulator tile) x one 64-column half of the F = 128 outputs; 2 CTAs per
-// tile meet through the ticket scheme of the CUDA-core kernel.  The CTA's half of the taps (fp16 hi | lo, no-swizzle
+// One CTA = 6 samples (60 node rows, one M = 64 accumulator tile) x one 64-column half of the F = 128 outputs; the 2 CTAs
+// of a tile are a thread-block cluster: the second one adds its partial logits into the first one's shared memory
+// (st.shared::cluster) and a cluster barrier replaces the global-memory ticket of the CUDA-core kernel.  The CTA's half of the taps (fp16 hi | lo, no-swizzle
 // K-major planes, 32 KB per tap) is fetched by bulk copies BEFORE the programmatic-launch wait, i.e. while the feature
 // kernel still runs -- with 22 CTAs at the benchmark size they sit on SMs the feature kernel does not use.  After the
 // wait: thread (sample, feature) reads its 10 node values, forms z_1 = x S and z_2 = z_1 S in registers, scales by the
@@ -37,7 +38,7 @@ struct GsSmem {
         s_off = off; off += GS_TS * GS_N * GS_N * 4;
         wa_off = off; off += 5 * 64 * 4;
         bias_off = off; off += 64 * 4;
-        part_off = off; off += 2 * 64 * 8 * 4;
+        part_off = off; off += 3 * 64 * 8 * 4;          // two 32-column parts of this CTA + the peer CTA's partial logits
         misc_off = off; off += 128;
         total = off;
     }
@@ -45,7 +46,7 @@ struct GsSmem {
 
 struct GsMisc {
     uint64_t w_full, mma_done;
-    uint32_t tmem_slot, is_last;
+    uint32_t tmem_slot, pad;
     uint32_t xmax[GS_TS];
     uint32_t colmax[GS_TS];
     float inv[GS_TS];
@@ -60,8 +61,6 @@ struct GsArgs {
     const float* wa;         // [5][128]
     const float* ba;         // [5]
     float* logits;           // [10][B][5]
-    float* lpart;            // [2][B*10][5]
-    unsigned int* tickets;   // [tiles], zero between launches
     int B, K, num_tiles, s_is_f64, pdl;
 };
 
@@ -94,7 +93,7 @@ __device__ __forceinline__ void gs_wait(uint64_t* bar, uint32_t parity, int id) 
 }
 
 template <int K>
-__global__ void __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArgs a) {
     extern __shared__ __align__(1024) unsigned char sm[];
     const GsSmem L(K);
     GsMisc* ms = reinterpret_cast<GsMisc*>(sm + L.misc_off);
@@ -276,32 +275,27 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gf_small_mma_kernel(const GsArg
         tcgen05_fence_before();
     }
     __syncthreads();
-    // ---- the two 32-column parts in a fixed order -> this CTA's partial logits; the second CTA of the tile to arrive
-    //      adds the two halves (half 0 first) and the bias of the action MLP
-    const size_t rows_total = (size_t)a.B * GS_N;
-    float* mine = a.lpart + (size_t)half * rows_total * 5;
-    for (int i = tid; i < nrows * 5; i += GS_THREADS) {
-        const int r = i / 5, q5 = i - r * 5;
-        mine[((size_t)b0 * GS_N + r) * 5 + q5] = part[r * 8 + q5] + part[(64 + r) * 8 + q5];
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned int t = atomicAdd(&a.tickets[tile], 1u);
-        ms->is_last = (t == 1u) ? 1u : 0u;
-        if (t == 1u) a.tickets[tile] = 0;        // ready for the next launch
-    }
-    __syncthreads();
-    if (ms->is_last) {
-        __threadfence();
-        const float* h0 = a.lpart;
-        const float* h1 = a.lpart + rows_total * 5;
+    // ---- the two 32-column parts in a fixed order -> this CTA's partial logits; CTA 1 of the pair hands its partial
+    //      logits to CTA 0 through distributed shared memory, CTA 0 adds the halves (half 0 first) and the action bias
+    float* peer = part + 2 * 64 * 8;
+    if (half == 1) {
         for (int i = tid; i < nrows * 5; i += GS_THREADS) {
             const int r = i / 5, q5 = i - r * 5;
-            const size_t gr = (size_t)b0 * GS_N + r;
+            const float v = part[r * 8 + q5] + part[(64 + r) * 8 + q5];
+            asm volatile(
+                "{\n\t.reg .b32 ra;\n\t"
+                "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+                "st.shared::cluster.f32 [ra], %1;\n\t}"
+                ::"r"(smem_u32(peer + r * 8 + q5)), "f"(v) : "memory");
+        }
+    }
+    cluster_sync_all();          // release / acquire at cluster scope: CTA 1's stores are visible to CTA 0
+    if (half == 0) {
+        for (int i = tid; i < nrows * 5; i += GS_THREADS) {
+            const int r = i / 5, q5 = i - r * 5;
             const int b = b0 + r / GS_N, n = r % GS_N;
             a.logits[((size_t)n * a.B + b) * 5 + q5] =
-                __ldcg(h0 + gr * 5 + q5) + __ldcg(h1 + gr * 5 + q5) + __ldg(a.ba + q5);
+                (part[r * 8 + q5] + part[(64 + r) * 8 + q5]) + peer[r * 8 + q5] + __ldg(a.ba + q5);
         }
     }
     tcgen05_fence_before();
@@ -366,12 +360,11 @@ static int gs_launch(const GsArgs& a, cudaStream_t st) {
 }
 
 int launch_gf_forward_small(const float* x, const void* S, int s_is_f64, const float* arena, const float* bias,
-                            const float* wa, const float* ba, float* logits, int B, int K, float* lpart,
-                            unsigned int* tickets, int pdl, cudaStream_t st) {
+                            const float* wa, const float* ba, float* logits, int B, int K, int pdl, cudaStream_t st) {
     GsArgs a;
     const unsigned char* base = reinterpret_cast<const unsigned char*>(arena);
     a.x = x; a.S = S; a.img = base; a.cst = reinterpret_cast<const float*>(base + (size_t)2 * K * 16 * GS_W_PLANE);
-    a.bias = bias; a.wa = wa; a.ba = ba; a.logits = logits; a.lpart = lpart; a.tickets = tickets;
+    a.bias = bias; a.wa = wa; a.ba = ba; a.logits = logits;
     a.B = B; a.K = K; a.num_tiles = (B + GS_TS - 1) / GS_TS; a.s_is_f64 = s_is_f64; a.pdl = pdl;
     if (K == 1) return gs_launch<1>(a, st);
     if (K == 2) return gs_launch<2>(a, st);

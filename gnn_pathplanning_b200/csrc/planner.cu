@@ -105,8 +105,7 @@ size_t gf_small_arena_bytes(int K);
 bool gf_small_supported(int N, int K);
 int launch_prep_gf_small(const float* w, float* arena, int K, cudaStream_t st);
 int launch_gf_forward_small(const float* x, const void* S, int s_is_f64, const float* arena, const float* bias,
-                            const float* wa, const float* ba, float* logits, int B, int K, float* lpart,
-                            unsigned int* tickets, int pdl, cudaStream_t st);
+                            const float* wa, const float* ba, float* logits, int B, int K, int pdl, cudaStream_t st);
 // im2col-free fp16-split tensor-core feature extractor (feature_mma.cu)
 size_t feature_mma_arena_floats();
 int launch_prep_feature_mma(const float* const* conv_w, const float* compress_w, const float* const* sc,
@@ -574,11 +573,8 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     // small batches at N = 10 (the benchmark configuration, rollout steps): 2 CTAs per 6 samples on the tensor core
     const bool use_small = !use_pair && p->gf_mode == 0 && gf_small_supported(N, p->K) && !debug_option(DBG_GF_MODE);
     if (use_small) {
-        rc = ensure_gf_scratch(p, rows, st);
-        if (rc) return rc;
         rc = launch_gf_forward_small(feat, S, s_is_f64, A + p->off_gfsmall, A + p->off_gfb, A + p->off_wa, A + p->off_ba,
-                                     logits, B, p->K, p->gf_lpart,
-                                     reinterpret_cast<unsigned int*>(p->gf_lpart + 10 * p->gf_lpart_rows), pdl, st);
+                                     logits, B, p->K, pdl, st);
     } else if (use_pair)
         rc = launch_gf_forward_pair(feat, S, s_is_f64, A + p->off_gfpair, A + p->off_gfb, nullptr, p->wa_host,
                                     p->wa_host + 640, logits, B, N, p->K, 1, st);
