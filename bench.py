@@ -55,12 +55,12 @@ WORKLOAD = "DCP K=3, 10 agents, 20x20 map, batch=64 inference per GPU (BASELINE.
 # SURVEY.md section 8d algorithmic figures
 FE_FLOPS_PER_AGENT_STEP = 2476224 + 32768          # 5 conv layers + compress MLP
 # DRAM traffic per unit from the committed ncu captures (dram__bytes_read.sum + dram__bytes_write.sum):
-#   profiles/r02_ncu_feature_mma_c2.csv: feature_mma_kernel per C2 launch (640 agent-steps); r01_ncu_full_summary_*.csv:
-#   gf_fwd_kernel 0.619 MB per C2 launch
-#   profiles/r02_ncu_pair_v13_summary.txt: gf_fwd_pair_kernel 664.35 MB for 65,536 episodes x 10 agents
+#   profiles/r02_ncu_feature_mma_c2.csv: feature_mma_kernel per C2 launch (640 agent-steps)
+#   profiles/r02_ncu_gf_small_c2.txt: gf_small_mma_kernel 0.593 MB per C2 launch
+#   profiles/r02_ncu_pair_v16_summary.txt: gf_fwd_pair_kernel 664.54 MB for 65,536 episodes x 10 agents
 NCU_FE_BYTES_PER_AGENT_STEP = 1.752576e6 / 640        # feature_mma_kernel: 0.93 MB of inputs + 0.63 MB of filter images + constants
-NCU_GF_BYTES_PER_AGENT_STEP = 0.619e6 / 640
-NCU_PAIR_BYTES_PER_AGENT_STEP = 664.35e6 / 655360
+NCU_GF_BYTES_PER_AGENT_STEP = 0.593408e6 / 640
+NCU_PAIR_BYTES_PER_AGENT_STEP = 664.54e6 / 655360
 
 
 def gf_bytes_per_agent_step(n):
@@ -352,7 +352,7 @@ def saturated_filter_roofline(gp, dev, batch, hbm_peak, peak_src):
                       "gpp_graph_filter_forward",
             "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "traffic": NCU_PAIR_BYTES_PER_AGENT_STEP * batch * N_AGENTS,
-            "traffic_source": "profiles/r02_ncu_pair_v13_summary.txt (dram read + write at 65,536 episodes, scaled by size)",
+            "traffic_source": "profiles/r02_ncu_pair_v16_summary.txt (dram read + write at 65,536 episodes, scaled by size)",
             "peak_source": peak_src, "mean_launch_us": sec * 1e6,
             "workload": "K=3, 10 agents, %d episodes (%.0f MB of node signals + GSOs in, %.0f MB out)"
                         % (batch, (batch * N_AGENTS * (128 + N_AGENTS) * 4) / 1e6, batch * N_AGENTS * 128 * 4 / 1e6),
@@ -731,11 +731,12 @@ def main():
                          "note": "640 agents = 80 tiles of 8 on 80 of 148 SMs, one tile per CTA: the launch is latency-bound "
                                  "(12 serialized MMA / epilogue phases per tile); the issued tensor work is 3x the algorithmic "
                                  "flops (split products) on M tiles that are 25-60 % padding"},
-            "roofline_graph_filter": {"kernel": "gf_fwd_kernel (K-tap filter + ReLU + action MLP, CUDA cores; the benchmark "
-                                                "size is launch-latency bound: 0.68 MB per launch)", "bound": "hbm",
+            "roofline_graph_filter": {"kernel": "gf_small_mma_kernel (K-tap filter + ReLU + action MLP on tcgen05, clusters "
+                                                "of 2 CTAs per 6 episodes; the benchmark size is launch-latency bound: 0.68 MB "
+                                                "per launch)", "bound": "hbm",
                                       "achieved": gf_gbs, "peak": hbm_peak, "unit": "GB/s",
                                       "frac": gf_gbs / hbm_peak, "traffic": NCU_GF_BYTES_PER_AGENT_STEP * agent_steps,
-                                      "traffic_source": "profiles/r01_ncu_full_summary_feature_gf.csv",
+                                      "traffic_source": "profiles/r02_ncu_gf_small_c2.txt",
                                       "peak_source": peak_src, "mean_launch_us": gf_s * 1e6,
                                       "algorithmic_bytes_per_launch": gf_bytes_per_agent_step(N_AGENTS) * agent_steps,
                                       "algorithmic_flops_per_launch": gf_flops_per_agent_step(N_AGENTS, K_TAPS) * agent_steps},

@@ -7,7 +7,8 @@ from oracle import planner_oracle as po
 class Cfg:
     def __init__(self, n, k): self.num_agents, self.nGraphFilterTaps, self.device = n, k, torch.device("cuda")
 def rel(a, b): return float(np.abs(a - b).max() / np.abs(b).max())
-for (N, K, B, fe, gf) in [(10, 3, 70, "mma", "cuda"), (7, 2, 3, "mma", "cuda"), (10, 3, 450, "mma", "pair"), (10, 3, 8, "cuda", "cuda")]:
+for (N, K, B, fe, gf) in [(10, 3, 70, "mma", "cuda"), (7, 2, 3, "mma", "cuda"), (10, 3, 450, "mma", "pair"), (10, 3, 8, "cuda", "cuda"),
+                          (10, 3, 64, "mma", "auto"), (10, 2, 7, "cuda", "auto"), (10, 1, 1, "cuda", "auto")]:   # auto at N = 10: gf_small_mma_kernel
     sd = po.init_state_dict(K, seed=N); po.randomize_bn_stats(sd, seed=B)
     x, S = synthetic.make_batch(B, N, 20, seed=B)
     m = gp.DecentralPlannerNet(Cfg(N, K)); m.load_state_dict(sd); m = m.cuda().eval()

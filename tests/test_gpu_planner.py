@@ -97,8 +97,8 @@ def test_eval_vs_oracle(N, K, B, map_w):
 
 
 def test_repeated_calls_with_changing_batch_sizes():
-    """One handle, many launches: small batches use the column-split filter launch whose tile tickets and
-    partial-logit scratch are reused across calls and regrown when the batch grows."""
+    """One handle, many launches: the filter kernel changes with the batch size (small-batch tcgen05 clusters below
+    4,096 node rows, the CTA-pair kernel above) and the per-handle scratch is regrown when the batch grows."""
     from gnn_pathplanning_b200 import synthetic
     from oracle import planner_oracle as po
     N, K, map_w = 10, 3, 20
