@@ -403,7 +403,12 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------------------
 # legs
 # ----------------------------------------------------------------------------------------------------------
-def leg_inference(gp, timer, dev, rank, world, n, k, batch, map_w, gso_dtype, K, warmup, pool_mb, label):
+def leg_inference(gp, timer, dev, rank, world, n, k, batch, map_w, gso_dtype, K, warmup, pool_mb, label, global_batch=None,
+                  cpu=False):
+    """`global_batch`: strong scaling -- the batch is the global one split evenly over the ranks (remainder dropped) and the
+    throughput is that of the whole job; otherwise `batch` episodes per GPU (weak)."""
+    if global_batch is not None:
+        batch = max(1, global_batch // world)
     sd = make_state_dict(k, seed=1000 + n)
     model = build_model(gp, sd, n, k, dev)
     xs_h, Ss_h = make_inputs(4, 4242 + 100 * rank + n, batch, n, map_w, gso_dtype)
@@ -417,7 +422,19 @@ def leg_inference(gp, timer, dev, rank, world, n, k, batch, map_w, gso_dtype, K,
     (ms,) = timer.max_over_ranks(ms)
     out = {"workload": label, "ms_per_step": ms / K, "us_per_step": 1e3 * ms / K,
            "agent_steps_per_s": world * batch * n * K / (ms * 1e-3), "windows": R, "gso_dtype": str(np.dtype(gso_dtype))}
-    if batch == 1:
+    if global_batch is not None:
+        out["scaling"] = "strong"
+        out["global_batch"] = batch * world
+        out["batch_per_gpu"] = batch
+    if cpu:
+        # the reference pins a rollout to one core (main.py:25-27) -- 1-thread and all-thread latency of the port
+        step_cpu = cpu_forward_factory(sd, xs_h, Ss_h)
+        for nthreads, key in ((1, "cpu_us_per_step_1_thread"), (usable_cpus(), "cpu_us_per_step_all_threads")):
+            torch.set_num_threads(nthreads)
+            n_cpu, el = time_cpu(step_cpu, 1.0)
+            out[key] = 1e6 * el / n_cpu
+        out["cpu_threads_all"] = usable_cpus()
+    if batch == 1 and global_batch is None:
         # the rollout step as the reference's agent runs it: host tensors in, logits out, one blocking call
         hx, hS = [t.pin_memory() for t in xs_h], [t.pin_memory() for t in Ss_h]
         hout = torch.empty(n, batch, 5).pin_memory()
@@ -680,9 +697,18 @@ def main():
     if not args.no_legs:
         with torch.no_grad():
             legs["C1_latency"] = leg_inference(gp, timer, dev, rank, world, 10, 2, 1, 20, np.float64, K, W, 8.0,
-                                               "DCP K=2, 10 agents, 20x20 map, batch=1 (configs[0]): rollout-step latency, float64 GSO")
+                                               "DCP K=2, 10 agents, 20x20 map, batch=1 (configs[0]): rollout-step latency, float64 GSO",
+                                               cpu=(rank == 0 and world == 1))
             legs["C4"] = leg_inference(gp, timer, dev, rank, world, 40, 3, 256, 50, np.float32, max(5, K // 4), W, args.pool_mb,
                                        "DCP K=3, 40 agents, 50x50 map, batch=256 inference per GPU (configs[3])")
+            if world > 1:
+                # SURVEY 8d asks for both scalings: the same global batch split over the ranks (the headline line is weak)
+                legs["C2_strong"] = leg_inference(gp, timer, dev, rank, world, 10, 3, 0, 20, np.float32, K, W, args.pool_mb,
+                                                  "configs[1] with its GLOBAL batch of 64 episodes split over %d GPUs" % world,
+                                                  global_batch=64)
+                legs["C4_strong"] = leg_inference(gp, timer, dev, rank, world, 40, 3, 0, 50, np.float32, max(5, K // 4), W,
+                                                  args.pool_mb, "configs[3] with its GLOBAL batch of 256 episodes split over %d "
+                                                  "GPUs" % world, global_batch=256)
             legs["rollout_C2"] = leg_rollout(gp, timer, dev, rank, world, 10, 3, 256, 20, max(5, K // 4), W,
                                              "256 device-resident episodes per GPU in lock-step (10 agents, 20x20 map, K=3): "
                                              "inputs builder + planner forward + move per step", rank == 0 and world == 1)
