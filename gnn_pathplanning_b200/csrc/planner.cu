@@ -131,7 +131,7 @@ using namespace gpp;
 static const int kConvC[6] = {3, 32, 32, 64, 64, 128};
 static const int IN_PIX = 3 * 11 * 11;
 
-constexpr int kStageSlots = 3;   // device staging slots of the pipelined host-buffer path (steps in flight)
+constexpr int kStageSlots = 6;   // device staging slots of the pipelined host-buffer path (steps in flight)
 
 struct gpp_planner {
     int K;
@@ -293,7 +293,8 @@ extern "C" int gpp_debug_feature_mma_timing(unsigned long long* out32) { return 
 // debug switches (include/gnnpp_b200_debug.h)
 extern "C" int gpp_debug_set_option(const char* name, int value) {
     GPP_REQUIRE(name, GPP_ERR_INVALID, "debug_set_option: null name");
-    static const char* const names[DBG_COUNT] = {"gf_timing", "tc_timing", "fe_timing", "no_pdl", "gf_mode", "pair_ablate"};
+    static const char* const names[DBG_COUNT] = {"gf_timing", "tc_timing", "fe_timing", "no_pdl", "gf_mode", "pair_ablate",
+                                                  "stage_mode"};
     for (int i = 0; i < DBG_COUNT; ++i)
         if (strcmp(name, names[i]) == 0) {
             g_debug_options[i] = value;
@@ -653,10 +654,10 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     const unsigned long long t = p->next_ticket;
     cudaEvent_t& ev = p->tickets[t % 16];
     if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    // Pipelined path: the inputs of this step are pulled over PCIe by a small staging kernel on a copy
-    // stream into one of three device slots while the kernels of the previous step run on the compute stream (a kernel that reads its
+    // Pipelined path: the inputs of this step are moved by the copy engine on a copy
+    // stream into one of kStageSlots device slots while the kernels of the previous steps run on the compute streams (a kernel that reads its
     // input straight over PCIe cannot overlap that read with its own compute); the logits are still
-    // written straight into the pinned host buffer.  Slot reuse waits for the step three tickets back.
+    // written straight into the pinned host buffer.  Slot reuse waits for the step kStageSlots tickets back.
     const int slot = (int)(t % kStageSlots);
     const size_t nx = (size_t)B * N * IN_PIX;
     const size_t sb = (size_t)B * N * N * (s_is_f64 ? 8 : 4);
@@ -681,13 +682,21 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
         GPP_CUDA_OK(cudaStreamWaitEvent(p->copy_stream, p->tickets[(t - kStageSlots) % 16], 0));
     {
         const size_t xb = sizeof(float) * nx;
-        StagePair sp;
-        sp.src[0] = reinterpret_cast<const uint4*>(mx); sp.dst[0] = reinterpret_cast<uint4*>(p->a_x[slot]);
-        sp.n16[0] = xb / 16; sp.tail[0] = (int)(xb % 16);
-        sp.src[1] = reinterpret_cast<const uint4*>(mS); sp.dst[1] = reinterpret_cast<uint4*>(p->a_S[slot]);
-        sp.n16[1] = sb / 16; sp.tail[1] = (int)(sb % 16);
-        stage_h2d_pair_kernel<<<16 + 1, 256, 0, p->copy_stream>>>(sp);
-        GPP_LAUNCH_CHECK();
+        // The copy engine moves the step's inputs (stable 35 us per step at 3-6 batches in flight, profiles/r02_e2e_lanes.txt);
+        // the staging kernel that round 1 used (a few CTAs pulling pinned memory with 16-byte loads) needs 5+ batches in
+        // flight to match it and is kept behind the "stage_mode" debug option for the probe.
+        if (debug_option(DBG_STAGE_MODE) == 0) {
+            GPP_CUDA_OK(cudaMemcpyAsync(p->a_x[slot], x_host, xb, cudaMemcpyHostToDevice, p->copy_stream));
+            GPP_CUDA_OK(cudaMemcpyAsync(p->a_S[slot], S_host, sb, cudaMemcpyHostToDevice, p->copy_stream));
+        } else {
+            StagePair sp;
+            sp.src[0] = reinterpret_cast<const uint4*>(mx); sp.dst[0] = reinterpret_cast<uint4*>(p->a_x[slot]);
+            sp.n16[0] = xb / 16; sp.tail[0] = (int)(xb % 16);
+            sp.src[1] = reinterpret_cast<const uint4*>(mS); sp.dst[1] = reinterpret_cast<uint4*>(p->a_S[slot]);
+            sp.n16[1] = sb / 16; sp.tail[1] = (int)(sb % 16);
+            stage_h2d_pair_kernel<<<16 + 1, 256, 0, p->copy_stream>>>(sp);
+            GPP_LAUNCH_CHECK();
+        }
     }
     GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));
     // two compute lanes (stream + feature workspace + filter scratch each), tickets alternate between them: the batches

@@ -12,8 +12,8 @@ xs, Ss = [], []
 for i in range(4):
     x, S = synthetic.make_batch(64, 10, 20, seed=10 + i)
     xs.append(torch.from_numpy(x).pin_memory()); Ss.append(torch.from_numpy(S).pin_memory())
-outs = [torch.empty(10, 64, 5).pin_memory() for _ in range(4)]
-def run(depth, steps=2000):
+outs = [torch.empty(10, 64, 5).pin_memory() for _ in range(8)]
+def run(depth, steps=4000):
     tk = []
     t0 = None
     for i in range(steps + 50):
@@ -23,11 +23,12 @@ def run(depth, steps=2000):
             torch.cuda.synchronize(); t0 = time.perf_counter()
         if len(tk) >= depth:
             m.wait(tk.pop(0))
-        tk.append(m.infer_host_async(xs[i % 4], Ss[i % 4], outs[i % 4]))
+        tk.append(m.infer_host_async(xs[i % 4], Ss[i % 4], outs[i % 8]))
     for t in tk: m.wait(t)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / steps * 1e6
-for nopdl in (0, 1):
-    _lib.set_debug_option("no_pdl", nopdl)
-    for depth in (2, 3, 4):
-        print("no_pdl=%d depth=%d: %.1f us/step  %.2f M agent-steps/s" % (nopdl, depth, run(depth), 640 / run(depth)), flush=True)
+for mode in (0, 1):          # staging: 0 = 17 x 256-thread copy kernel, 1 = copy engine, n >= 2 = n x 512-thread copy kernel
+    _lib.set_debug_option("stage_mode", mode)
+    for depth in (3, 4, 5, 6):
+        us = run(depth)
+        print("stage_mode=%d depth=%d: %.1f us/step  %.2f M agent-steps/s  (H2D %.1f GB/s)" % (mode, depth, us, 640 / us, 954880 / us * 1e-3), flush=True)
