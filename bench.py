@@ -17,7 +17,7 @@ through a device pool larger than L2.
 
 value   C2 device-resident (inputs already in HBM).
 e2e     C2 through the public host-buffer call: every step's x / S cross PCIe from pinned host memory and
-        its logits come back, inside the timed region.  `value` = 4 independent episode batches in flight
+        its logits come back, inside the timed region.  `value` = 6 independent episode batches in flight (`value_3_in_flight`: 3)
         (DecentralPlannerNet.infer_host_async / wait), `sync_value` = one blocking call per step.
 legs    the other BASELINE.json configs, same timing rules: C1 (K=2, batch 1, float64 GSO: rollout-step
         latency), C4 (40 agents, 50x50 map, batch 256), train_C3 (K=3, 10 agents, batch 64: forward + fused
@@ -667,27 +667,30 @@ def main():
         # (a) one blocking host call per step
         sync_ms, sync_R = timer.host_windows(lambda i: model.infer_host(hx[i % unique], hS[i % unique], hout), K, W,
                                              lambda: None)
-        # (b) pipelined over independent episode batches (depth 4): step i is enqueued before step i-3 is waited
-        # for, as a rollout driver advancing four batches of episodes in turn would do; every step still reads
-        # its x / S from pinned host memory and writes its logits back to it
-        DEPTH = 4
-        houts = [torch.empty(N_AGENTS, BATCH, 5).pin_memory() for _ in range(DEPTH)]
-        inflight, sink = [], [0.0]
+        # (b) pipelined over independent episode batches: step i is enqueued before step i - (DEPTH - 1) is waited for, as
+        # a rollout driver advancing DEPTH groups of episodes in turn would do; every step still reads its x / S from
+        # pinned host memory and writes its logits back to it.  The library rotates the tickets over 4 compute lanes.
+        def pipelined(depth):
+            houts = [torch.empty(N_AGENTS, BATCH, 5).pin_memory() for _ in range(depth)]
+            inflight, sink = [], [0.0]
 
-        def async_step(i):
-            inflight.append((model.infer_host_async(hx[i % unique], hS[i % unique], houts[i % DEPTH]), i % DEPTH))
-            if len(inflight) >= DEPTH:
-                tk, slot = inflight.pop(0)
-                model.wait(tk)
-                sink[0] += float(houts[slot][0, 0, 0])       # the step's result is read on the host
+            def async_step(i):
+                inflight.append((model.infer_host_async(hx[i % unique], hS[i % unique], houts[i % depth]), i % depth))
+                if len(inflight) >= depth:
+                    tk, slot = inflight.pop(0)
+                    model.wait(tk)
+                    sink[0] += float(houts[slot][0, 0, 0])       # the step's result is read on the host
 
-        def drain():
-            while inflight:
-                tk, slot = inflight.pop(0)
-                model.wait(tk)
-                sink[0] += float(houts[slot][0, 0, 0])
-        e2e_ms, e2e_R = timer.host_windows(async_step, K, W, drain)
-    ms, e2e_ms, sync_ms = timer.max_over_ranks(ms, e2e_ms, sync_ms)
+            def drain():
+                while inflight:
+                    tk, slot = inflight.pop(0)
+                    model.wait(tk)
+                    sink[0] += float(houts[slot][0, 0, 0])
+            return timer.host_windows(async_step, K, W, drain)
+        DEPTH = 6
+        e2e_ms, e2e_R = pipelined(DEPTH)
+        e2e3_ms, _ = pipelined(3)
+    ms, e2e_ms, sync_ms, e2e3_ms = timer.max_over_ranks(ms, e2e_ms, sync_ms, e2e3_ms)
     clocks = sampler.summary()
 
     agent_steps = BATCH * N_AGENTS
@@ -738,9 +741,11 @@ def main():
             "e2e": {"value": world * agent_steps * K / (e2e_ms * 1e-3), "unit": UNIT, "steps": K, "windows": e2e_R,
                     "h2d_bytes_per_step": bytes_per_batch, "d2h_bytes_per_step": N_AGENTS * BATCH * 5 * 4,
                     "api": "DecentralPlannerNet.infer_host_async/wait -> gpp_planner_forward_host_async (pinned host "
-                           "buffers; inputs staged by the copy engine on a copy stream, forward on one of two compute "
-                           "lanes so one batch's CNN overlaps the previous batch's graph filter, logits written straight to "
-                           "host), 4 independent episode batches in flight",
+                           "buffers; inputs staged by the copy engine on a copy stream, forward on one of four compute "
+                           "lanes so one batch's CNN runs next to other batches' kernels on the SMs a 640-agent launch leaves "
+                           "idle, logits written straight to host), %d independent episode batches in flight" % DEPTH,
+                    "batches_in_flight": DEPTH,
+                    "value_3_in_flight": world * agent_steps * K / (e2e3_ms * 1e-3),
                     "sync_value": world * agent_steps * K / (sync_ms * 1e-3), "sync_windows": sync_R,
                     "sync_api": "DecentralPlannerNet.infer_host -> gpp_planner_forward_host, one blocking call per step"},
             "gpu_launches": int(launches_per_window) * R, "gpu_launches_per_step": int(launches_per_window) / K,

@@ -41,7 +41,7 @@ extern std::atomic<unsigned long long> g_launches;
 int sm_count();       // SM count of the CURRENT device (cached per device ordinal)
 
 // Debug switches (include/gnnpp_b200_debug.h: gpp_debug_set_option); all 0 in production.
-enum DebugOption { DBG_GF_TIMING = 0, DBG_TC_TIMING = 1, DBG_FE_TIMING = 2, DBG_NO_PDL = 3, DBG_GF_MODE = 4, DBG_PAIR_ABLATE = 5, DBG_STAGE_MODE = 6, DBG_COUNT = 7 };
+enum DebugOption { DBG_GF_TIMING = 0, DBG_TC_TIMING = 1, DBG_FE_TIMING = 2, DBG_NO_PDL = 3, DBG_GF_MODE = 4, DBG_PAIR_ABLATE = 5, DBG_STAGE_MODE = 6, DBG_LANES = 7, DBG_COUNT = 8 };
 int debug_option(int which);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device function attribute: remember the largest

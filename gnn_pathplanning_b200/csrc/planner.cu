@@ -131,7 +131,8 @@ using namespace gpp;
 static const int kConvC[6] = {3, 32, 32, 64, 64, 128};
 static const int IN_PIX = 3 * 11 * 11;
 
-constexpr int kStageSlots = 6;   // device staging slots of the pipelined host-buffer path (steps in flight)
+constexpr int kLanes = 4;        // compute lanes of the pipelined host-buffer path
+constexpr int kStageSlots = 8;   // device staging slots of the pipelined host-buffer path (steps in flight)
 
 struct gpp_planner {
     int K;
@@ -154,12 +155,14 @@ struct gpp_planner {
     bool weights_set;
     float* raw;          // device staging for host-provided parameters
     size_t raw_floats;
-    // second compute lane of the pipelined host path (gpp_planner_forward_host_async alternates between two streams
-    // so that the feature kernel of one batch overlaps the graph-filter kernel of the batch before it): its own stream
-    // and scratch; swapped in for the duration of a call by LaneGuard
-    cudaStream_t stream2;
+    // extra compute lanes of the pipelined host path (gpp_planner_forward_host_async rotates over kLanes streams so that
+    // the feature kernel of one batch overlaps the graph-filter kernel of the batch before it and the idle SMs of a
+    // 640-agent launch take the next batch's tiles): own stream and scratch each; swapped in for the duration of a call by
+    // LaneGuard.  Lane 0 is the handle's own stream and scratch.
+    cudaStream_t lane_stream[kLanes - 1];
     bool lanes_active;   // inside gpp_planner_forward_host_async
-    float* feat2; size_t feat_rows2; float* gf_lpart2; size_t gf_lpart_rows2; bool pdl_ok2;
+    float* lane_feat[kLanes - 1]; size_t lane_feat_rows[kLanes - 1]; float* lane_lpart[kLanes - 1];
+    size_t lane_lpart_rows[kLanes - 1]; bool lane_pdl_ok[kLanes - 1];
     float* feat;         // [rows][128] workspace
     size_t feat_rows;
     const void* alias_host[16];   // pinned host buffers seen by the async entry point and their device aliases
@@ -256,9 +259,11 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->raw);
     cudaFree(p->feat);
     cudaFree(p->gf_lpart);
-    cudaFree(p->feat2);
-    cudaFree(p->gf_lpart2);
-    if (p->stream2) cudaStreamDestroy(p->stream2);
+    for (int l = 0; l < kLanes - 1; ++l) {
+        cudaFree(p->lane_feat[l]);
+        cudaFree(p->lane_lpart[l]);
+        if (p->lane_stream[l]) cudaStreamDestroy(p->lane_stream[l]);
+    }
     cudaFree(p->d_x);
     cudaFree(p->d_S);
     cudaFree(p->d_logits);
@@ -294,7 +299,7 @@ extern "C" int gpp_debug_feature_mma_timing(unsigned long long* out32) { return 
 extern "C" int gpp_debug_set_option(const char* name, int value) {
     GPP_REQUIRE(name, GPP_ERR_INVALID, "debug_set_option: null name");
     static const char* const names[DBG_COUNT] = {"gf_timing", "tc_timing", "fe_timing", "no_pdl", "gf_mode", "pair_ablate",
-                                                  "stage_mode"};
+                                                  "stage_mode", "lanes"};
     for (int i = 0; i < DBG_COUNT; ++i)
         if (strcmp(name, names[i]) == 0) {
             g_debug_options[i] = value;
@@ -381,7 +386,8 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
         int rc0 = order_after_previous_stream(p, st);
         if (rc0) return rc0;
     }
-    if (p->stream2) GPP_CUDA_OK(cudaStreamSynchronize(p->stream2));    // batches in flight on the second lane read the arena
+    for (int l = 0; l < kLanes - 1; ++l)      // batches in flight on the other lanes read the arena
+        if (p->lane_stream[l]) GPP_CUDA_OK(cudaStreamSynchronize(p->lane_stream[l]));
     gpp_planner_weights d = *w;
     const int K = p->K;
     if (!on_device) {
@@ -446,7 +452,7 @@ extern "C" int gpp_planner_set_weights(gpp_planner* p, const gpp_planner_weights
     if (rc) return rc;
     rc = launch_split_taps(A + p->off_gfw, A + p->off_gfws, K * 128, st);
     p->pdl_ok = false;
-    p->pdl_ok2 = false;
+    for (int l = 0; l < kLanes - 1; ++l) p->lane_pdl_ok[l] = false;
     if (rc) return rc;
     rc = launch_prep_umma_taps(d.gf_w, A + p->off_gfimg, K, st);
     if (rc) return rc;
@@ -500,16 +506,16 @@ static int ensure_gf_scratch(gpp_planner* p, size_t rows, cudaStream_t st) {
 
 // x / S / logits may be device memory or pinned host memory mapped into the device address space
 // (zero-copy); `allow_bulk` = 0 keeps the filter kernel off the bulk-copy engine for host-mapped S.
-struct LaneGuard {       // lane 1: the handle's scratch fields point at the second lane's buffers inside the call
+struct LaneGuard {       // lane l > 0: the handle's scratch fields point at that lane's buffers inside the call
     gpp_planner* p;
-    bool on;
+    int l;
     void swap_in_out() {
-        std::swap(p->feat, p->feat2); std::swap(p->feat_rows, p->feat_rows2);
-        std::swap(p->gf_lpart, p->gf_lpart2); std::swap(p->gf_lpart_rows, p->gf_lpart_rows2);
-        std::swap(p->pdl_ok, p->pdl_ok2);
+        std::swap(p->feat, p->lane_feat[l]); std::swap(p->feat_rows, p->lane_feat_rows[l]);
+        std::swap(p->gf_lpart, p->lane_lpart[l]); std::swap(p->gf_lpart_rows, p->lane_lpart_rows[l]);
+        std::swap(p->pdl_ok, p->lane_pdl_ok[l]);
     }
-    LaneGuard(gpp_planner* pl, int lane) : p(pl), on(lane != 0) { if (on) swap_in_out(); }
-    ~LaneGuard() { if (on) swap_in_out(); }
+    LaneGuard(gpp_planner* pl, int lane) : p(pl), l(lane - 1) { if (l >= 0) swap_in_out(); }
+    ~LaneGuard() { if (l >= 0) swap_in_out(); }
 };
 
 static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, int s_is_f64,
@@ -517,7 +523,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
                                 cudaStream_t st, int lane = 0) {
     const size_t rows = (size_t)B * N;
     LaneGuard lane_guard(p, lane);
-    if (lane == 0) {       // lane 1's scratch is only ever used on its own stream
+    if (lane == 0) {       // the other lanes' scratch is only ever used on their own streams
         int rc0 = order_after_previous_stream(p, st);
         if (rc0) return rc0;
     }
@@ -532,7 +538,7 @@ static int planner_forward_impl(gpp_planner* p, const float* x, const void* S, i
     fa.x = x; fa.feat = feat; fa.total_agents = (int)rows; fa.apt = 0; fa.num_tiles = 0; fa.timing = nullptr;
     // programmatic dependent launch: each kernel's prologue (barriers, filter prefetch) overlaps the tail of the
     // kernel before it; not for the first forward after the weights changed (the prologue reads them)
-    // ... and not on the two-lane pipelined host path: a dependent kernel launched early parks its CTAs (and their shared
+    // ... and not on the multi-lane pipelined host path: a dependent kernel launched early parks its CTAs (and their shared
     // memory) on the SMs the other lane's kernel should be using (45.0 vs 48.4 us per step, profiles/r02_e2e_lanes.txt)
     const int pdl = (!debug_option(DBG_NO_PDL) && p->pdl_ok && !p->profiling && !p->lanes_active) ? 1 : 0;
     fa.pdl = pdl;
@@ -665,7 +671,8 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     if (!p->copied[slot]) GPP_CUDA_OK(cudaEventCreateWithFlags(&p->copied[slot], cudaEventDisableTiming));
     if (p->a_x_floats[slot] < nx || p->a_S_bytes[slot] < sb) {
         GPP_CUDA_OK(cudaStreamSynchronize(p->stream));
-        if (p->stream2) GPP_CUDA_OK(cudaStreamSynchronize(p->stream2));
+        for (int l = 0; l < kLanes - 1; ++l)
+            if (p->lane_stream[l]) GPP_CUDA_OK(cudaStreamSynchronize(p->lane_stream[l]));
         GPP_CUDA_OK(cudaStreamSynchronize(p->copy_stream));
         if (p->a_x_floats[slot] < nx) {
             cudaFree(p->a_x[slot]); p->a_x[slot] = nullptr; p->a_x_floats[slot] = 0;
@@ -699,12 +706,14 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
         }
     }
     GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));
-    // two compute lanes (stream + feature workspace + filter scratch each), tickets alternate between them: the batches
+    // kLanes compute lanes (stream + feature workspace + filter scratch each), tickets rotate over them: the batches
     // are independent, so the feature kernel of ticket t+1 (80 of 148 SMs at the benchmark size) runs next to the
     // graph-filter kernel of ticket t instead of behind it
-    const int lane = (int)(t & 1);
-    if (lane && !p->stream2) GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking));
-    cudaStream_t cst = lane ? p->stream2 : p->stream;
+    const int nlanes = debug_option(DBG_LANES) >= 1 && debug_option(DBG_LANES) <= kLanes ? debug_option(DBG_LANES) : kLanes;
+    const int lane = (int)(t % (unsigned long long)nlanes);
+    if (lane && !p->lane_stream[lane - 1])
+        GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->lane_stream[lane - 1], cudaStreamNonBlocking));
+    cudaStream_t cst = lane ? p->lane_stream[lane - 1] : p->stream;
     GPP_CUDA_OK(cudaStreamWaitEvent(cst, p->copied[slot], 0));
     p->lanes_active = true;
     int rc = planner_forward_impl(p, p->a_x[slot], p->a_S[slot], s_is_f64, reinterpret_cast<float*>(ml),

@@ -402,7 +402,7 @@ class DecentralPlannerNet(nn.Module):
         """Pipelined variant of `infer_host` for rollouts over several independent episode batches:
         enqueues the zero-copy forward and returns a ticket at once; `wait(ticket)` blocks until that
         step's logits are in `out_host`.  All three tensors must be pinned and must not be touched in
-        between.  The batches must be independent: consecutive tickets run on two compute streams and may finish
+        between.  The batches must be independent: consecutive tickets run on four compute streams in rotation and may finish
         in either order."""
         assert not self.training, "infer_host_async is the eval-mode rollout path"
         # (pinned-ness and alignment are checked by the C entry point; this is the per-step hot path)

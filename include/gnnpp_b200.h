@@ -224,8 +224,8 @@ int gpp_rollout_move(const float* logits, int* pos, const int* goal, const unsig
                      int W, void* stream);
 
 /* Asynchronous variant for pipelined rollouts over INDEPENDENT episode batches: stages the inputs on a copy stream,
- * enqueues the forward on one of the planner's two compute streams (tickets alternate, so the feature kernel of one
- * batch runs next to the graph-filter kernel of the batch before it) and returns at once with a completion ticket; the
+ * enqueues the forward on one of the planner's four compute streams (tickets rotate over them, so the feature kernel of
+ * one batch runs next to the kernels of the batches before it on the SMs they leave idle) and returns at once with a completion ticket; the
  * host buffers MUST be pinned and must stay untouched until gpp_planner_wait(ticket) returns.  Consecutive tickets may
  * complete in either order -- wait for the ticket whose logits are needed; at most 16 tickets may be outstanding. */
 int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const void* S_host,

@@ -27,8 +27,11 @@ def run(depth, steps=4000):
     for t in tk: m.wait(t)
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / steps * 1e6
-for mode in (0, 1):          # staging: 0 = 17 x 256-thread copy kernel, 1 = copy engine, n >= 2 = n x 512-thread copy kernel
+for lanes in (3, 4):
+  _lib.set_debug_option("lanes", lanes)
+  print("compute lanes:", lanes, flush=True)
+  for mode in (0,):          # staging: 0 = copy engine (default), 1 = the 17 x 256-thread copy kernel
     _lib.set_debug_option("stage_mode", mode)
-    for depth in (3, 4, 5, 6):
+    for depth in (6, 8):
         us = run(depth)
         print("stage_mode=%d depth=%d: %.1f us/step  %.2f M agent-steps/s  (H2D %.1f GB/s)" % (mode, depth, us, 640 / us, 954880 / us * 1e-3), flush=True)
