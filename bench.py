@@ -15,7 +15,8 @@ maximum a measure of submission jitter in round 1).  A rank's figure is the MEDI
 figure the MAX over ranks of that, after a barrier + torch.cuda.synchronize() on both sides.  Inputs rotate
 through a device pool larger than L2.
 
-value   C2 device-resident (inputs already in HBM).
+value   C2 device-resident (inputs already in HBM), 6 independent episode batches in flight over the library's compute
+        lanes (DecentralPlannerNet.infer_async / join); `single_stream` = the same steps one after the other on one stream.
 e2e     C2 through the public host-buffer call: every step's x / S cross PCIe from pinned host memory and
         its logits come back, inside the timed region.  `value` = 6 independent episode batches in flight (`value_3_in_flight`: 3)
         (DecentralPlannerNet.infer_host_async / wait), `sync_value` = one blocking call per step.
@@ -235,15 +236,20 @@ class Timer:
             self.dist.barrier()
         torch.cuda.synchronize()
 
-    def device_windows(self, step, K, warmup):
-        """step(i) enqueues one step on the current stream.  Returns (median window ms on this rank, windows)."""
+    def device_windows(self, step, K, warmup, drain=None):
+        """step(i) enqueues one step on the current stream (or on the library's lanes: then drain() makes the current
+        stream wait for everything outstanding before a window's closing event).  Returns (median window ms on this
+        rank, windows)."""
+        drain = drain or (lambda: None)
         for i in range(warmup):
             step(i)
+        drain()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(K):
             step(warmup + i)
+        drain()
         e1.record()
         torch.cuda.synchronize()
         probe = max(e0.elapsed_time(e1), 1e-3)
@@ -255,6 +261,7 @@ class Timer:
             a.record()
             for i in range(K):
                 step(n + i)
+            drain()
             b.record()
             n += K
         torch.cuda.synchronize()
@@ -647,7 +654,24 @@ def main():
             dev_step(i)
         torch.cuda.synchronize()
         launches_per_window = _lib.launch_count()      # library kernels in one K-step window
-        ms, R = timer.device_windows(dev_step, K, W)
+        single_ms, single_R = timer.device_windows(dev_step, K, W)      # one stream, one batch after the other
+        # the same steps as a driver of independent episode batches issues them: DEV_DEPTH batches in flight over the
+        # library's compute lanes (DecentralPlannerNet.infer_async / join), device tensors in, device logits out; the
+        # closing event of a window waits for every outstanding step
+        DEV_DEPTH = 6
+        dev_outs = [torch.empty(N_AGENTS, BATCH, 5, device=dev) for _ in range(DEV_DEPTH)]
+        dev_inflight = []
+
+        def dev_async_step(i):
+            tk, _ = model.infer_async(pool_x[i % pool_n], pool_S[i % pool_n], dev_outs[i % DEV_DEPTH])
+            dev_inflight.append(tk)
+            if len(dev_inflight) >= DEV_DEPTH:
+                model.join(dev_inflight.pop(0))
+
+        def dev_drain():
+            while dev_inflight:
+                model.join(dev_inflight.pop(0))
+        ms, R = timer.device_windows(dev_async_step, K, W, dev_drain)
 
         # ---- per-kernel durations (events recorded around each kernel; PDL is off in this pass) -------
         nat = model._native_for(dev)
@@ -690,7 +714,7 @@ def main():
         DEPTH = 6
         e2e_ms, e2e_R = pipelined(DEPTH)
         e2e3_ms, _ = pipelined(3)
-    ms, e2e_ms, sync_ms, e2e3_ms = timer.max_over_ranks(ms, e2e_ms, sync_ms, e2e3_ms)
+    ms, e2e_ms, sync_ms, e2e3_ms, single_ms = timer.max_over_ranks(ms, e2e_ms, sync_ms, e2e3_ms, single_ms)
     clocks = sampler.summary()
 
     agent_steps = BATCH * N_AGENTS
@@ -738,6 +762,12 @@ def main():
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg,
+            "value_api": "DecentralPlannerNet.infer_async / join -> gpp_planner_forward_async: device tensors in, device logits "
+                         "out, %d independent episode batches in flight over the library's 4 compute lanes" % DEV_DEPTH,
+            "single_stream": {"value": world * agent_steps * K / (single_ms * 1e-3), "ms_per_step": single_ms / K,
+                              "windows": single_R,
+                              "api": "model.addGSO(S); model(x) on one stream, one batch after the other (the latency "
+                                     "of a step; kernels chained by programmatic dependent launch)"},
             "e2e": {"value": world * agent_steps * K / (e2e_ms * 1e-3), "unit": UNIT, "steps": K, "windows": e2e_R,
                     "h2d_bytes_per_step": bytes_per_batch, "d2h_bytes_per_step": N_AGENTS * BATCH * 5 * 4,
                     "api": "DecentralPlannerNet.infer_host_async/wait -> gpp_planner_forward_host_async (pinned host "

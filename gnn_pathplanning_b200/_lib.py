@@ -38,7 +38,7 @@ EXPORTED = (
     "gpp_planner_create", "gpp_planner_destroy", "gpp_planner_set_weights",
     "gpp_planner_forward", "gpp_planner_forward_host",
     "gpp_planner_train_workspace_bytes", "gpp_planner_train_forward", "gpp_planner_train_backward", "gpp_planner_ce_loss", "gpp_rollout_build_inputs", "gpp_rollout_move",
-    "gpp_planner_forward_host_async", "gpp_planner_wait",
+    "gpp_planner_forward_host_async", "gpp_planner_wait", "gpp_planner_forward_async", "gpp_planner_join",
     "gpp_planner_set_profiling", "gpp_planner_get_profile",
     "gpp_planner_set_graph_filter_mode", "gpp_planner_set_feature_mode",
     "gpp_launch_count", "gpp_reset_launch_count",
@@ -185,6 +185,10 @@ def load():
         lib.gpp_planner_forward_host_async.argtypes = [vp, vp, vp, i, vp, i, i, C.POINTER(C.c_ulonglong)]
         lib.gpp_planner_wait.restype = i
         lib.gpp_planner_wait.argtypes = [vp, C.c_ulonglong]
+        lib.gpp_planner_forward_async.restype = i
+        lib.gpp_planner_forward_async.argtypes = [vp, vp, vp, i, vp, i, i, vp, C.POINTER(C.c_ulonglong)]
+        lib.gpp_planner_join.restype = i
+        lib.gpp_planner_join.argtypes = [vp, C.c_ulonglong, vp]
         lib.gpp_debug_tc_timing.restype = i
         lib.gpp_debug_tc_timing.argtypes = [C.POINTER(C.c_ulonglong)]
         lib.gpp_debug_pair_timing.restype = i

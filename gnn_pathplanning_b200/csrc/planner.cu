@@ -180,6 +180,7 @@ struct gpp_planner {
     size_t d_logits_floats;
     // asynchronous host-buffer calls: completion tickets + double-buffered H2D staging on a copy stream
     cudaEvent_t tickets[16];
+    cudaEvent_t ready[16];       // gpp_planner_forward_async: the caller's stream at submission
     unsigned long long next_ticket;
     cudaStream_t copy_stream;
     float* a_x[kStageSlots];
@@ -269,8 +270,10 @@ extern "C" void gpp_planner_destroy(gpp_planner* p) {
     cudaFree(p->d_logits);
     if (p->stream) cudaStreamDestroy(p->stream);
     if (p->order_event) cudaEventDestroy(p->order_event);
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 16; ++i) {
         if (p->tickets[i]) cudaEventDestroy(p->tickets[i]);
+        if (p->ready[i]) cudaEventDestroy(p->ready[i]);
+    }
     for (int i = 0; i < kStageSlots; ++i) {
         cudaFree(p->a_x[i]);
         cudaFree(p->a_S[i]);
@@ -643,6 +646,30 @@ static void* mapped_alias_cached(gpp_planner* p, const void* host_ptr) {
     return d;
 }
 
+// kLanes compute lanes (stream + feature workspace + filter scratch each), tickets rotate over them: the batches are
+// independent, so the feature kernel of ticket t+1 (80 of 148 SMs at the benchmark size) runs next to the kernels of
+// the tickets before it instead of behind them.  `ready`: the inputs are complete once this event has fired.
+static int enqueue_on_lane(gpp_planner* p, const float* x, const void* S, int s_is_f64, float* logits, int B, int N,
+                           cudaEvent_t ready, unsigned long long* ticket) {
+    const unsigned long long t = p->next_ticket;
+    cudaEvent_t& ev = p->tickets[t % 16];
+    if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    const int nlanes = debug_option(DBG_LANES) >= 1 && debug_option(DBG_LANES) <= kLanes ? debug_option(DBG_LANES) : kLanes;
+    const int lane = (int)(t % (unsigned long long)nlanes);
+    if (lane && !p->lane_stream[lane - 1])
+        GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->lane_stream[lane - 1], cudaStreamNonBlocking));
+    cudaStream_t cst = lane ? p->lane_stream[lane - 1] : p->stream;
+    GPP_CUDA_OK(cudaStreamWaitEvent(cst, ready, 0));
+    p->lanes_active = true;
+    int rc = planner_forward_impl(p, x, S, s_is_f64, logits, nullptr, B, N, 1, cst, lane);
+    p->lanes_active = false;
+    if (rc) return rc;
+    GPP_CUDA_OK(cudaEventRecord(ev, cst));
+    p->next_ticket = t + 1;
+    *ticket = t;
+    return GPP_OK;
+}
+
 extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const void* S_host,
                                               int s_is_f64, float* logits_host, int B, int N,
                                               unsigned long long* ticket) {
@@ -658,8 +685,6 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
     GPP_REQUIRE((reinterpret_cast<uintptr_t>(mx) & 15u) == 0 && (reinterpret_cast<uintptr_t>(mS) & 15u) == 0,
                 GPP_ERR_INVALID, "planner_forward_host_async: host buffers must be 16-byte aligned");
     const unsigned long long t = p->next_ticket;
-    cudaEvent_t& ev = p->tickets[t % 16];
-    if (!ev) GPP_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     // Pipelined path: the inputs of this step are moved by the copy engine on a copy
     // stream into one of kStageSlots device slots while the kernels of the previous steps run on the compute streams (a kernel that reads its
     // input straight over PCIe cannot overlap that read with its own compute); the logits are still
@@ -706,23 +731,27 @@ extern "C" int gpp_planner_forward_host_async(gpp_planner* p, const float* x_hos
         }
     }
     GPP_CUDA_OK(cudaEventRecord(p->copied[slot], p->copy_stream));
-    // kLanes compute lanes (stream + feature workspace + filter scratch each), tickets rotate over them: the batches
-    // are independent, so the feature kernel of ticket t+1 (80 of 148 SMs at the benchmark size) runs next to the
-    // graph-filter kernel of ticket t instead of behind it
-    const int nlanes = debug_option(DBG_LANES) >= 1 && debug_option(DBG_LANES) <= kLanes ? debug_option(DBG_LANES) : kLanes;
-    const int lane = (int)(t % (unsigned long long)nlanes);
-    if (lane && !p->lane_stream[lane - 1])
-        GPP_CUDA_OK(cudaStreamCreateWithFlags(&p->lane_stream[lane - 1], cudaStreamNonBlocking));
-    cudaStream_t cst = lane ? p->lane_stream[lane - 1] : p->stream;
-    GPP_CUDA_OK(cudaStreamWaitEvent(cst, p->copied[slot], 0));
-    p->lanes_active = true;
-    int rc = planner_forward_impl(p, p->a_x[slot], p->a_S[slot], s_is_f64, reinterpret_cast<float*>(ml),
-                                  nullptr, B, N, 1, cst, lane);
-    p->lanes_active = false;
-    if (rc) return rc;
-    GPP_CUDA_OK(cudaEventRecord(ev, cst));
-    p->next_ticket = t + 1;
-    *ticket = t;
+    return enqueue_on_lane(p, p->a_x[slot], p->a_S[slot], s_is_f64, reinterpret_cast<float*>(ml), B, N, p->copied[slot], ticket);
+}
+
+extern "C" int gpp_planner_forward_async(gpp_planner* p, const float* x, const void* S, int s_is_f64, float* logits,
+                                         int B, int N, void* stream, unsigned long long* ticket) {
+    GPP_REQUIRE(p && x && S && logits && ticket, GPP_ERR_INVALID, "planner_forward_async: null pointer");
+    DeviceGuard guard(p->device);
+    GPP_REQUIRE(p->weights_set, GPP_ERR_INVALID, "planner_forward_async: gpp_planner_set_weights not called");
+    GPP_REQUIRE(B >= 1 && N >= 1 && N <= 64, GPP_ERR_INVALID, "planner_forward_async: bad sizes B=%d N=%d", B, N);
+    cudaEvent_t& rd = p->ready[p->next_ticket % 16];
+    if (!rd) GPP_CUDA_OK(cudaEventCreateWithFlags(&rd, cudaEventDisableTiming));
+    GPP_CUDA_OK(cudaEventRecord(rd, reinterpret_cast<cudaStream_t>(stream)));     // x and S are ready behind this point
+    return enqueue_on_lane(p, x, S, s_is_f64, logits, B, N, rd, ticket);
+}
+
+extern "C" int gpp_planner_join(gpp_planner* p, unsigned long long ticket, void* stream) {
+    GPP_REQUIRE(p, GPP_ERR_INVALID, "planner_join: null planner");
+    DeviceGuard guard(p->device);
+    GPP_REQUIRE(ticket < p->next_ticket && ticket + 16 >= p->next_ticket, GPP_ERR_INVALID,
+                "planner_join: ticket %llu is not among the 16 most recent calls", ticket);
+    GPP_CUDA_OK(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(stream), p->tickets[ticket % 16], 0));
     return GPP_OK;
 }
 

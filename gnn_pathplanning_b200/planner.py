@@ -435,6 +435,42 @@ class DecentralPlannerNet(nn.Module):
         self.__dict__["_async_native"] = nat
         return int(t.value)
 
+    def infer_async(self, x: torch.Tensor, S: torch.Tensor, out: torch.Tensor = None):
+        """Pipelined forward on DEVICE tensors for drivers that advance several independent episode batches: x
+        [B,N,3,11,11] f32 and S [B,N,N] f32/f64 as produced on the current stream; the forward is enqueued on the next of
+        the library's compute lanes and `(ticket, out)` returns at once.  `join(ticket)` makes the current stream wait for
+        that step's logits `out` [N,B,5] (device-side, the host does not block), `wait(ticket)` blocks the host.  x, S and
+        out must stay untouched until then.  Same arithmetic as `addGSO(S); forward(x)` in eval mode
+        (/root/reference/graphs/models/decentralplanner.py:266-318)."""
+        assert not self.training, "infer_async is the eval-mode rollout path"
+        _require_cuda(x, "x")
+        _require_cuda(S, "S")
+        assert x.dtype == torch.float32 and x.is_contiguous() and S.is_contiguous() and S.device == x.device
+        assert S.dim() == 3 and S.dtype in (torch.float32, torch.float64)
+        B, N = x.shape[0], x.shape[1]
+        assert N == self.numAgents and tuple(S.shape) == (B, N, N)
+        if out is None:
+            out = torch.empty(N, B, 5, device=x.device, dtype=torch.float32)
+        assert out.device == x.device and tuple(out.shape) == (N, B, 5) and out.dtype == torch.float32 and out.is_contiguous()
+        nat = self._native_for(x.device)
+        if getattr(nat, "fresh", False):                  # weight re-layout ran on torch's stream: the lanes start behind it
+            torch.cuda.current_stream(x.device).synchronize()
+            nat.fresh = False
+        t = C.c_ulonglong()
+        _lib.check(nat.lib.gpp_planner_forward_async(
+            nat.handle, x.data_ptr(), S.data_ptr(), int(S.dtype == torch.float64), out.data_ptr(), B, N,
+            torch.cuda.current_stream(x.device).cuda_stream, C.byref(t)))
+        self.__dict__["_async_native"] = nat
+        self.__dict__["_async_device"] = x.device
+        return int(t.value), out
+
+    def join(self, ticket: int) -> None:
+        """The current stream of the device waits for `ticket` (see `infer_async`)."""
+        nat = self.__dict__["_async_native"]
+        dev = self.__dict__.get("_async_device")
+        stream = torch.cuda.current_stream(dev) if dev is not None else torch.cuda.current_stream()
+        _lib.check(nat.lib.gpp_planner_join(nat.handle, C.c_ulonglong(ticket), stream.cuda_stream))
+
     def _key_tensors_device(self):
         return self.__dict__["_key_tensors"][0].device
 

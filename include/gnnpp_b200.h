@@ -233,6 +233,17 @@ int gpp_planner_forward_host_async(gpp_planner* p, const float* x_host, const vo
                                    unsigned long long* ticket);
 int gpp_planner_wait(gpp_planner* p, unsigned long long ticket);
 
+/* The same pipelining for DEVICE tensors (a driver advancing several independent episode batches whose inputs are produced on
+ * the GPU): x / S must be complete in `stream` order at the time of the call (an event is recorded there), the forward
+ * runs on the next compute lane, and the logits (device memory, [N][B][5]) may be consumed after
+ * gpp_planner_join(p, ticket, consumer_stream) -- a device-side wait, the host does not block -- or after
+ * gpp_planner_wait(ticket).  x, S and logits must stay untouched until then; tickets share the numbering and the limit of
+ * 16 outstanding calls with gpp_planner_forward_host_async.  Replaces a loop of `model.addGSO(S); model(x)` calls
+ * (/root/reference/agents/decentralplannerlocal.py:576-588) over independent batches. */
+int gpp_planner_forward_async(gpp_planner* p, const float* x, const void* S, int s_is_f64, float* logits, int B, int N,
+                              void* stream, unsigned long long* ticket);
+int gpp_planner_join(gpp_planner* p, unsigned long long ticket, void* stream);
+
 /* Which graph-filter kernel the planner uses: 0 = automatic (tensor cores once B*N >= 4096 node
  * rows), 1 = CUDA-core fp32 kernel (gf_fwd_kernel), 2 = tcgen05 3xTF32 kernel (gf_fwd_tc_kernel),
  * 3 = tcgen05 CTA-pair fp16-split kernel (gf_fwd_pair_kernel).  GPP_ERR_UNSUPPORTED at forward

@@ -101,3 +101,45 @@ def test_host_buffer_entry_points_use_the_same_kernel():
     for t, o in zip(tickets, outs):
         m.wait(t)
         assert rel_err(o.numpy(), ref) <= TOL
+
+
+def test_device_async_pipeline_matches_oracle_and_sequential_calls():
+    """infer_async / join (gpp_planner_forward_async): independent batches of different sizes in flight over the library's
+    compute lanes, device tensors in and out, interleaved with ordinary forward calls on the same module."""
+    from gnn_pathplanning_b200 import synthetic
+    from oracle import planner_oracle as po
+    K = 3
+    sd = po.init_state_dict(K, seed=21)
+    po.randomize_bn_stats(sd, seed=22)
+    m = _model(sd, K)
+    m.set_graph_filter_mode("auto")
+    sizes = [64, 7, 64, 450, 1, 64, 13, 64, 64, 30, 64, 64]          # 450 x 10 rows: the CTA-pair filter kernel
+    batches, refs = [], []
+    for i, B in enumerate(sizes):
+        x, S = synthetic.make_batch(B, 10, 20, seed=500 + i)
+        if i % 3 == 1:
+            S = S.astype(np.float64)
+        xt, St = torch.from_numpy(x), torch.from_numpy(S)
+        with torch.no_grad():
+            refs.append(torch.stack(po.planner_forward(sd, St, xt)).numpy())
+        batches.append((xt.cuda(), St.cuda()))
+    torch.cuda.synchronize()
+    inflight, outs = [], [None] * len(sizes)
+    with torch.no_grad():
+        for i, (xd, Sd) in enumerate(batches):
+            tk, out = m.infer_async(xd, Sd)
+            inflight.append((tk, i, out))
+            if i == 5:                                   # a plain call in the middle of the pipeline
+                m.addGSO(batches[0][1])
+                mid = torch.stack(m(batches[0][0])).cpu().numpy()
+                assert rel_err(mid, refs[0]) <= TOL
+            if len(inflight) >= 6:
+                tk0, j, o = inflight.pop(0)
+                m.join(tk0)                              # device-side wait on the current stream
+                outs[j] = o.clone()
+        for tk0, j, o in inflight:
+            m.wait(tk0)                                  # host-side wait
+            outs[j] = o.clone()
+    torch.cuda.synchronize()
+    for j, B in enumerate(sizes):
+        assert rel_err(outs[j].cpu().numpy(), refs[j]) <= TOL, (j, B)
