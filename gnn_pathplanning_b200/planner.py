@@ -29,6 +29,14 @@ import torch.nn as nn
 from . import _lib
 from .graphml import GraphFilterBatch, _require_cuda
 
+
+def _raw_stream(device) -> int:
+    """cudaStream_t of torch's current stream on `device` as an integer (per-step hot path: the raw accessor avoids
+    building a torch.cuda.Stream object)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    return get(idx) if get is not None else torch.cuda.current_stream(idx).cuda_stream
+
 _CONV_CH = [3, 32, 32, 64, 64, 128]
 _CONV_IDX = (0, 4, 7, 11, 14)
 
@@ -371,7 +379,7 @@ class DecentralPlannerNet(nn.Module):
         # the C entry point switches to the handle's device itself; the stream is the tensor's device's current one
         _lib.check(nat.lib.gpp_planner_forward(
             nat.handle, x.data_ptr(), S3.data_ptr(), int(S3.dtype == torch.float64),
-            logits.data_ptr(), None, B, N, torch.cuda.current_stream(x.device).cuda_stream))
+            logits.data_ptr(), None, B, N, _raw_stream(x.device)))
         return logits
 
     def infer_host(self, x_host: torch.Tensor, S_host: torch.Tensor, out_host: torch.Tensor = None,
@@ -459,7 +467,7 @@ class DecentralPlannerNet(nn.Module):
         t = C.c_ulonglong()
         _lib.check(nat.lib.gpp_planner_forward_async(
             nat.handle, x.data_ptr(), S.data_ptr(), int(S.dtype == torch.float64), out.data_ptr(), B, N,
-            torch.cuda.current_stream(x.device).cuda_stream, C.byref(t)))
+            _raw_stream(x.device), C.byref(t)))
         self.__dict__["_async_native"] = nat
         self.__dict__["_async_device"] = x.device
         return int(t.value), out
@@ -467,9 +475,8 @@ class DecentralPlannerNet(nn.Module):
     def join(self, ticket: int) -> None:
         """The current stream of the device waits for `ticket` (see `infer_async`)."""
         nat = self.__dict__["_async_native"]
-        dev = self.__dict__.get("_async_device")
-        stream = torch.cuda.current_stream(dev) if dev is not None else torch.cuda.current_stream()
-        _lib.check(nat.lib.gpp_planner_join(nat.handle, C.c_ulonglong(ticket), stream.cuda_stream))
+        dev = self.__dict__.get("_async_device") or torch.device("cuda", torch.cuda.current_device())
+        _lib.check(nat.lib.gpp_planner_join(nat.handle, C.c_ulonglong(ticket), _raw_stream(dev)))
 
     def _key_tensors_device(self):
         return self.__dict__["_key_tensors"][0].device
