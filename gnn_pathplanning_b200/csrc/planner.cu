@@ -67,16 +67,9 @@ int launch_gf_forward_pair(const float* x, const void* S, int s_is_f64, const vo
                            const float* wa_host, const float* ba_host, float* logits, int B, int N, int K, int relu,
                            cudaStream_t st);
 
-// Host -> device staging as a kernel: a few CTAs pull pinned (device-mapped) host memory over PCIe with
-// 16-byte loads and store it to HBM.  Runs on the copy stream next to the compute kernels of the previous
-// step (they leave SMs free at rollout batch sizes); n16 = number of 16-byte units, tail bytes separately.
-__global__ void __launch_bounds__(256) stage_h2d_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
-                                                        size_t n16, const unsigned char* src_tail,
-                                                        unsigned char* dst_tail, int tail) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
-    if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
-}
+// Host -> device staging as a kernel (probe path of gpp_planner_forward_host_async, "stage_mode" debug option; the
+// production path uses the copy engine): a few CTAs pull pinned (device-mapped) host memory over PCIe with 16-byte loads
+// and store it to HBM; n16 = number of 16-byte units, tail bytes separately.
 // both inputs of a step in one launch: blocks [0, gridDim.x - 1) copy x, the last block copies S
 struct StagePair {
     const uint4* src[2];
