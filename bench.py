@@ -175,6 +175,34 @@ def cpu_forward_factory(sd, xs, Ss):
     return step
 
 
+def cpu_infer_arm(n, k, batch, map_w, steps):
+    """CPU port (oracle) on one of the other BASELINE configs: agent-steps/s of `steps` inference steps after one warm-up."""
+    from oracle import planner_oracle as po
+    sd = make_state_dict(k, seed=1000 + n)
+    xs, Ss = make_inputs(1, 9200 + n, batch, n, map_w)
+    with torch.no_grad():
+        po.planner_forward(sd, Ss[0], xs[0])
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            po.planner_forward(sd, Ss[0], xs[0])
+    return steps * batch * n / (time.perf_counter() - t0)
+
+
+def cpu_train_arm(sd, n, batch, map_w, steps):
+    """CPU port (oracle) train step -- forward + loss + backward, no optimizer -- agent-steps/s."""
+    from oracle import planner_oracle as po
+    from gnn_pathplanning_b200 import synthetic
+    x, S = synthetic.make_batch(batch, n, map_w, seed=9000 + n)
+    tg = torch.from_numpy(synthetic.random_targets(batch, n, seed=9100 + n))
+    leaf = {k2: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k2) else v)
+            for k2, v in sd.items()}
+    bn = {k2: v.clone() for k2, v in sd.items() if "running" in k2 or "tracked" in k2}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        po.planner_loss(po.planner_forward(leaf, torch.from_numpy(S), torch.from_numpy(x), True, bn), tg).backward()
+    return steps * batch * n / (time.perf_counter() - t0)
+
+
 def usable_cpus():
     """CPUs this process may really use: affinity mask capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -822,19 +850,20 @@ def main():
             with torch.no_grad():
                 got = torch.stack(model(xs_h[0].to(dev))).cpu().numpy()
             line["parity_max_rel"] = float(np.abs(got - ref).max() / np.abs(ref).max())
-            if legs and "train_C3" in legs:
-                # CPU arm of the training leg: the oracle's train step (forward + loss + backward; no optimizer), 3 steps
-                from oracle import planner_oracle as po
-                from gnn_pathplanning_b200 import synthetic
-                x, S = synthetic.make_batch(64, 10, 20, seed=9000)
-                tg = torch.from_numpy(synthetic.random_targets(64, 10, seed=9100))
-                leaf = {k2: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k2) else v)
-                        for k2, v in sd.items()}
-                bn = {k2: v.clone() for k2, v in sd.items() if "running" in k2 or "tracked" in k2}
-                t0 = time.perf_counter()
-                for _ in range(3):
-                    po.planner_loss(po.planner_forward(leaf, torch.from_numpy(S), torch.from_numpy(x), True, bn), tg).backward()
-                legs["train_C3"]["cpu_baseline_agent_steps_per_s"] = 3 * 640 / (time.perf_counter() - t0)
+            # CPU arms of the other legs (the port timed on every configuration), bounded samples, the thread
+            # count chosen above; a failure here must not cost the line
+            try:
+                if legs and "train_C3" in legs:
+                    legs["train_C3"]["cpu_baseline_agent_steps_per_s"] = cpu_train_arm(sd, 10, 64, 20, 3)
+                if legs and "C4" in legs:
+                    legs["C4"]["cpu_baseline_agent_steps_per_s"] = cpu_infer_arm(40, 3, 256, 50, 2)
+                if legs and "train_C5_shard" in legs:
+                    legs["train_C5_shard"]["cpu_baseline_agent_steps_per_s"] = cpu_train_arm(sd, 20, 64, 28, 2)
+                if legs:
+                    line["legs_cpu_arm"] = {"kind": "port", "cores": threads,
+                                            "sample": "3 / 2 / 2 steps of train_C3 / C4 / train_C5_shard"}
+            except Exception as e:       # noqa: BLE001
+                line["cpu_arms_error"] = repr(e)[:200]
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
