@@ -17,7 +17,10 @@ extern "C" {
  *   "gf_mode"    kernel choice of the standalone gpp_graph_filter_forward: 0 auto, 1 CUDA-core, 2 tcgen05 3xTF32,
  *                3 tcgen05 CTA-pair fp16-split
  *   "pair_ablate" (performance experiments only, results are wrong) bit mask for the CTA-pair kernel: 1 skip the
- *                propagations, 2 skip the operand stores, 4 skip the x loads, 8 skip the y stores */
+ *                propagations, 2 skip the operand stores, 4 skip the x loads, 8 skip the y stores
+ *   "stage_mode" (probe) input staging of gpp_planner_forward_host_async: 0 copy engine (production), != 0 the copy
+ *                kernel that pulls pinned memory with 16-byte loads (profiles/r02_e2e_lanes.txt)
+ *   "lanes"      (probe) compute lanes used by the pipelined entry points: 1 .. 4, 0 = all four */
 int gpp_debug_set_option(const char* name, int value);
 
 /* Test hook for the tcgen05 plumbing: D[128][128] = A[128][32] . B[128][32]^T on the tensor cores
